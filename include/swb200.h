@@ -1,0 +1,144 @@
+/*
+ * swb200.h -- C ABI of the B200-native Smith-Waterman fill / backtrack path.
+ *
+ * The reference (chunhualiao/Smith-Waterman) has no library interface; its hot
+ * path is reached through
+ *   (1) the per-cell helpers  similarityScore(i,j,H,P,&maxPos) / backtrack(P,maxPos)
+ *       driven by the nDiag wavefront loop in main()      (omp_smithW.c:52-54,203-216,331-420)
+ *   (2) the whole-fill operator of the rotated variants
+ *       smithWaterman(a,b,w,h,H,P,&maxloc)                 (rotated-cuda/sw-rotated-cuda-unified.cu:198-215,
+ *                                                           rotated-cuda/sw-rotated-omp.cc:192-209)
+ *   (3) the CLI  ./omp_smithW <number_of_col> <number_of_rows>   (omp_smithW.c:8,91-96)
+ * Every entry point below names the reference interface it replaces.  All of
+ * them return 0 on success and a negative swb_status otherwise (the reference
+ * prints and exit(0)s on CUDA errors, simple-cuda/sw-default-discrete.cu:101-108;
+ * we never exit).  No global state; calls on different streams/devices are
+ * independent.  There is NO CPU fallback: without a CUDA device every compute
+ * entry point returns SWB_ERR_CUDA.
+ *
+ * Data contract (identical to the reference, omp_smithW.c:109-118,336):
+ *   a: m bytes (columns), b: n bytes (rows)
+ *   H, P: (n+1) x pitch int32, row-major, pitch >= m+1 (reference: pitch == m+1),
+ *         row 0 and column 0 are zero and ARE written by the fill (the caller's
+ *         buffers need not be initialised, as in (2))
+ *   P codes NONE 0, UP 1, LEFT 2, DIAGONAL 3 (omp_smithW.c:33-36); backtrack
+ *   multiplies the path cells by -1 (omp_smithW.c:32,417)
+ *   maxPos = pitch*i + j of the first cell, in the reference's scan order
+ *   (anti-diagonal ascending, then row descending), that attains the global
+ *   maximum; 0 if no score is positive (omp_smithW.c:173,384-387)
+ */
+#ifndef SWB200_H
+#define SWB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SWB_OK            =  0,
+    SWB_ERR_ARG       = -1,   /* null pointer, non-positive size, pitch < m+1 ...          */
+    SWB_ERR_ALIGN     = -2,   /* dH/dP not 16-byte aligned                                 */
+    SWB_ERR_CUDA      = -3,   /* a CUDA call failed (see swb_last_cuda_error)              */
+    SWB_ERR_RANGE     = -4,   /* sizes/scores outside what 32-bit packed scores can hold   */
+    SWB_ERR_NOMEM     = -5    /* device or pinned-host allocation failed                   */
+} swb_status;
+
+/* omp_smithW.c:75-77 (matchScore, missmatchScore, gapScore); NULL means 3,-3,-2 */
+typedef struct { int32_t match, mismatch, gap; } swb_scoring;
+
+/* parameters.h:1-2 of the reference; kept for CLI / log compatibility only */
+#define SWB_FACTOR 128
+#define SWB_CUTOFF 1024
+
+/* Tuning knobs (0 = library default).  Not part of the reference surface. */
+typedef struct swb_timer swb_timer;   /* CUDA-event pair around the fill kernel only */
+typedef struct {
+    int32_t warps_per_band;   /* warps (32-row strips) per CTA band, 1..16          */
+    int32_t reserved[5];
+    swb_timer* timer;         /* if set, swb_fill_async brackets the fill kernel launch with its events */
+} swb_tuning;
+
+/* Kernel-only timing for the roofline figure: events are recorded on the call's stream
+ * immediately before/after the fill kernel launch (not the prep/argmax kernels). */
+int  swb_timer_create(swb_timer** t, int device);
+int  swb_timer_elapsed_ms(swb_timer* t, float* ms);   /* synchronises on the stop event */
+void swb_timer_destroy(swb_timer* t);
+
+const char* swb_strerror(int status);
+const char* swb_last_cuda_error(void);          /* thread-local text of the last CUDA failure */
+int  swb_version(void);
+int  swb_device_count(void);
+
+/* ---- device-pointer API (the kernel boundary) --------------------------------
+ * Replaces the nDiag loop + similarityScore (omp_smithW.c:203-216,331-388) and
+ * smithWaterman() of the rotated variants.
+ *   a, b      : host OR device pointers (detected); m = cols, n = rows
+ *   dH, dP    : caller-owned DEVICE buffers, (n+1)*pitch int32 each, 16-byte aligned
+ *   d_maxPos  : DEVICE int64 (may be NULL), written asynchronously
+ *   stream    : cudaStream_t (NULL = default stream); the call only enqueues work
+ */
+int swb_fill_async(const char* a, int64_t m, const char* b, int64_t n,
+                   const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch,
+                   int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream,
+                   const swb_tuning* tuning);
+
+/* Same, but synchronises the stream and returns maxPos / maxScore to the host. */
+int swb_fill(const char* a, int64_t m, const char* b, int64_t n,
+             const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch,
+             int64_t* maxPos, int device, void* stream);
+
+/* Replaces backtrack(P, maxPos) (omp_smithW.c:405-420): negates P along the path
+ * in place on the device.  maxPos == 0 (no positive score) is a defined no-op
+ * (the reference has undefined behaviour there).  d_maxPos, when non-NULL, is a
+ * DEVICE pointer read on the stream (chain after swb_fill_async without a sync)
+ * and takes precedence over maxPos.  d_pathLen: DEVICE int64 or NULL. */
+int swb_backtrack_async(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_t* d_maxPos,
+                        int64_t* d_pathLen, int device, void* stream);
+int swb_backtrack(int32_t* dP, int64_t pitch, int64_t maxPos, int64_t* path_len,
+                  int device, void* stream);
+
+/* ---- host-buffer API (what a caller of the reference program would bind) -----
+ * One call = the timed region of simple-cuda/sw-default-discrete.cu:382-444
+ * (H2D of a,b; fill; D2H of the matrices) plus backtrack.  H and P are HOST
+ * buffers of (n+1)*(m+1) int32 (pitch m+1); either may be NULL to skip its
+ * copy-back.  P is returned AFTER backtrack when do_backtrack != 0. */
+int swb_align_host(const char* a, int64_t m, const char* b, int64_t n,
+                   const swb_scoring* scoring, int32_t* H, int32_t* P,
+                   int64_t* maxPos, int64_t* path_len, int do_backtrack, int device);
+
+/* Reusable context for repeated host-buffer calls of one shape (keeps the device
+ * matrices and workspace alive between calls; swb_align_host creates/destroys
+ * one internally). */
+typedef struct swb_ctx swb_ctx;
+int  swb_ctx_create(swb_ctx** ctx, int64_t m, int64_t n, int device);
+int  swb_ctx_align(swb_ctx* ctx, const char* a, const char* b, const swb_scoring* scoring,
+                   int32_t* H, int32_t* P, int64_t* maxPos, int64_t* path_len, int do_backtrack);
+int32_t* swb_ctx_dH(swb_ctx* ctx);
+int32_t* swb_ctx_dP(swb_ctx* ctx);
+void swb_ctx_destroy(swb_ctx* ctx);
+
+/* Score-only variant (no H/P stores): max score and maxPos with the reference
+ * tie-break.  Replaces the -DSKIP_BACKTRACK style runs of the reference's
+ * variants (omp_smithW-v1-refinedOrig.cpp:190-192) for callers that only need
+ * the score. */
+int swb_score_only(const char* a, int64_t m, const char* b, int64_t n,
+                   const swb_scoring* scoring, int32_t* maxScore, int64_t* maxPos,
+                   int device, void* stream);
+
+/* The reference's generate() (omp_smithW.c:489-519): srand(seed) then m+1 draws
+ * for a and n+1 draws for b with this libc's rand(), 0->A 2->C 3->G else T.
+ * Host-side helper so that callers get the reference's sequences for a seed. */
+void swb_generate(unsigned seed, int64_t m, int64_t n, char* a, char* b);
+
+/* Pinned host memory for the host-buffer API (the D2H of H and P dominates an
+ * end-to-end call; pageable buffers halve its rate).  NULL on failure. */
+void* swb_host_alloc(size_t bytes);
+void  swb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWB200_H */

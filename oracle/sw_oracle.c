@@ -129,6 +129,37 @@ void swo_fill_rowmajor(const char *a, int64_t m, const char *b, int64_t n,
     *maxPos = gmax > 0 ? M * bi + bj : 0;
 }
 
+void swo_fill_block(const char *a, int64_t m, const char *b, int64_t i0, int64_t i1,
+                    const swo_scoring *sc, const int32_t *Htop, int32_t *Hblk, int32_t *Pblk,
+                    int32_t *best /* in/out: score, */, int64_t *best_i, int64_t *best_j)
+{
+    /* rows i0..i1-1 (1-based matrix rows) of the same recurrence as swo_fill_rowmajor,
+     * continuing from row i0-1 given in Htop (m+1 ints).  Hblk/Pblk hold (i1-i0) rows. */
+    const int64_t M = m + 1;
+    int32_t gmax = *best;
+    int64_t bi = *best_i, bj = *best_j;
+    for (int64_t i = i0; i < i1; ++i) {
+        const int32_t *up = (i == i0) ? Htop : Hblk + (i - i0 - 1) * M;
+        int32_t *hr = Hblk + (i - i0) * M, *pr = Pblk + (i - i0) * M;
+        hr[0] = 0; pr[0] = 0;
+        for (int64_t j = 1; j < M; ++j) {
+            int32_t sub = (a[j - 1] == b[i - 1]) ? sc->match : sc->mismatch;
+            int32_t d = up[j - 1] + sub, u = up[j] + sc->gap, l = hr[j - 1] + sc->gap;
+            int32_t h = 0, pred = P_NONE;
+            if (d > h) { h = d; pred = P_DIAGONAL; }
+            if (u > h) { h = u; pred = P_UP; }
+            if (l > h) { h = l; pred = P_LEFT; }
+            hr[j] = h; pr[j] = pred;
+            if (h > gmax ||
+                (h == gmax && h > 0 &&
+                 (i + j < bi + bj || (i + j == bi + bj && i > bi)))) {
+                gmax = h; bi = i; bj = j;
+            }
+        }
+    }
+    *best = gmax; *best_i = bi; *best_j = bj;
+}
+
 int64_t swo_backtrack(int32_t *P, int64_t pitch, int64_t maxPos)
 {
     /* omp_smithW.c:405-420 */

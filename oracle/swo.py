@@ -67,6 +67,10 @@ class Oracle:
         L.swo_score_only.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(Scoring),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.swo_score_only.restype = None
+        L.swo_fill_block.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Scoring),
+                                     _i32p, _i32p, _i32p, C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int64)]
+        L.swo_fill_block.restype = None
         L.swo_nelement.argtypes = [C.c_int64] * 3
         L.swo_nelement.restype = C.c_int64
 
@@ -87,6 +91,25 @@ class Oracle:
         fn = self.lib.swo_fill_wavefront if order == "wavefront" else self.lib.swo_fill_rowmajor
         fn(a.ctypes.data, m, b.ctypes.data, n, C.byref(sc), H.reshape(-1), P.reshape(-1), C.byref(mp))
         return H, P, int(mp.value)
+
+    def fill_blocks(self, a, b, block_rows: int = 1024, scoring=DEFAULT_SCORING):
+        """Generator over row blocks: yields (i0, i1, Hblk, Pblk) for rows i0..i1-1 (row 0
+        excluded) and finally returns through .maxPos on the generator's last item:
+        the last yield is (None, None, maxScore, maxPos)."""
+        a = _as_bytes(a); b = _as_bytes(b)
+        m, n = len(a), len(b)
+        sc = Scoring(*scoring)
+        top = np.zeros(m + 1, dtype=np.int32)
+        best, bi, bj = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+        for i0 in range(1, n + 1, block_rows):
+            i1 = min(i0 + block_rows, n + 1)
+            Hb = np.empty((i1 - i0, m + 1), dtype=np.int32)
+            Pb = np.empty((i1 - i0, m + 1), dtype=np.int32)
+            self.lib.swo_fill_block(a.ctypes.data, m, b.ctypes.data, i0, i1, C.byref(sc), top,
+                                    Hb.reshape(-1), Pb.reshape(-1), C.byref(best), C.byref(bi), C.byref(bj))
+            top = Hb[-1].copy()
+            yield i0, i1, Hb, Pb
+        yield None, None, int(best.value), (int(bi.value) * (m + 1) + int(bj.value)) if best.value > 0 else 0
 
     def backtrack(self, P: np.ndarray, maxPos: int) -> int:
         """negates the path in place; returns its length"""

@@ -1,0 +1,249 @@
+"""smith-waterman_b200 -- host-side mirror of the reference's hot-path interface.
+
+Thin ctypes layer over the C ABI in include/swb200.h (libswb200.so, hand-written
+sm_100a CUDA).  There is no CPU fallback: importing works without a GPU (so the
+symbol table can be checked), every compute call needs a CUDA device and raises
+`SwbError` otherwise.  PyTorch is used by callers only for device memory and
+streams; nothing here imports it.
+
+Reference interfaces mirrored (chunhualiao/Smith-Waterman):
+  smithWaterman(a, b, w, h, H, P, &maxloc)      rotated-cuda/sw-rotated-cuda-unified.cu:198-215
+  similarityScore / nDiag loop, backtrack       omp_smithW.c:203-216,331-388,405-420
+  generate()                                    omp_smithW.c:489-519
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+__all__ = ["lib", "SwbError", "Scoring", "DEFAULT_SCORING", "generate", "fill", "fill_async", "backtrack",
+           "smithWaterman", "align_host", "AlignContext", "score_only", "KernelTimer", "host_alloc", "host_free",
+           "device_count", "LIB_PATH", "NONE", "UP", "LEFT", "DIAGONAL", "PATH"]
+
+# omp_smithW.c:32-36
+PATH, NONE, UP, LEFT, DIAGONAL = -1, 0, 1, 2, 3
+
+LIB_PATH = Path(__file__).resolve().parent / "libswb200.so"
+
+
+class SwbError(RuntimeError):
+    pass
+
+
+class Scoring(C.Structure):
+    """omp_smithW.c:75-77"""
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap", C.c_int32)]
+
+
+class Tuning(C.Structure):
+    _fields_ = [("warps_per_band", C.c_int32), ("reserved", C.c_int32 * 5), ("timer", C.c_void_p)]
+
+
+DEFAULT_SCORING = (3, -3, -2)
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise SwbError(f"{LIB_PATH} is missing: build it with `make -C smith-waterman_b200` "
+                       "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+    L = C.CDLL(str(LIB_PATH))
+    i64, i32, vp = C.c_int64, C.c_int32, C.c_void_p
+    L.swb_strerror.argtypes = [C.c_int]; L.swb_strerror.restype = C.c_char_p
+    L.swb_last_cuda_error.argtypes = []; L.swb_last_cuda_error.restype = C.c_char_p
+    L.swb_version.restype = C.c_int
+    L.swb_device_count.restype = C.c_int
+    L.swb_fill_async.argtypes = [vp, i64, vp, i64, C.POINTER(Scoring), vp, vp, i64, vp, vp, C.c_int, vp,
+                                 C.POINTER(Tuning)]
+    L.swb_fill.argtypes = [vp, i64, vp, i64, C.POINTER(Scoring), vp, vp, i64, C.POINTER(i64), C.c_int, vp]
+    L.swb_backtrack_async.argtypes = [vp, i64, i64, vp, vp, C.c_int, vp]
+    L.swb_backtrack.argtypes = [vp, i64, i64, C.POINTER(i64), C.c_int, vp]
+    L.swb_align_host.argtypes = [vp, i64, vp, i64, C.POINTER(Scoring), vp, vp, C.POINTER(i64), C.POINTER(i64),
+                                 C.c_int, C.c_int]
+    L.swb_ctx_create.argtypes = [C.POINTER(vp), i64, i64, C.c_int]
+    L.swb_ctx_align.argtypes = [vp, vp, vp, C.POINTER(Scoring), vp, vp, C.POINTER(i64), C.POINTER(i64), C.c_int]
+    L.swb_ctx_dH.argtypes = [vp]; L.swb_ctx_dH.restype = vp
+    L.swb_ctx_dP.argtypes = [vp]; L.swb_ctx_dP.restype = vp
+    L.swb_ctx_destroy.argtypes = [vp]; L.swb_ctx_destroy.restype = None
+    L.swb_score_only.argtypes = [vp, i64, vp, i64, C.POINTER(Scoring), C.POINTER(i32), C.POINTER(i64), C.c_int, vp]
+    L.swb_generate.argtypes = [C.c_uint, i64, i64, vp, vp]; L.swb_generate.restype = None
+    L.swb_timer_create.argtypes = [C.POINTER(vp), C.c_int]; L.swb_timer_create.restype = C.c_int
+    L.swb_timer_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]; L.swb_timer_elapsed_ms.restype = C.c_int
+    L.swb_timer_destroy.argtypes = [vp]; L.swb_timer_destroy.restype = None
+    L.swb_host_alloc.argtypes = [C.c_size_t]; L.swb_host_alloc.restype = vp
+    L.swb_host_free.argtypes = [vp]; L.swb_host_free.restype = None
+    for name in ("swb_fill_async", "swb_fill", "swb_backtrack_async", "swb_backtrack", "swb_align_host",
+                 "swb_ctx_create", "swb_ctx_align", "swb_score_only"):
+        getattr(L, name).restype = C.c_int
+    return L
+
+
+lib = _load()
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        msg = lib.swb_strerror(rc).decode()
+        detail = lib.swb_last_cuda_error().decode()
+        raise SwbError(f"swb200: {msg} (status {rc})" + (f": {detail}" if rc in (-3, -5) and detail else ""))
+
+
+def _scoring(sc) -> Scoring:
+    return sc if isinstance(sc, Scoring) else Scoring(*(sc or DEFAULT_SCORING))
+
+
+def _ptr(x) -> int:
+    """raw address of a torch tensor / numpy array / int / bytes-like"""
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    if isinstance(x, bytes):            # points into x itself; the caller keeps x alive over the call
+        return C.cast(C.c_char_p(x), C.c_void_p).value
+    if isinstance(x, bytearray):
+        return C.addressof((C.c_char * len(x)).from_buffer(x))
+    raise TypeError(f"cannot take the address of {type(x)}")
+
+
+def _stream_ptr(stream) -> int:
+    if stream is None:
+        return 0
+    return getattr(stream, "cuda_stream", stream)
+
+
+def device_count() -> int:
+    return int(lib.swb_device_count())
+
+
+def generate(seed: int, m: int, n: int):
+    """The reference's generate() for a pinned seed -> (a, b) as bytes."""
+    a = C.create_string_buffer(max(m, 1))
+    b = C.create_string_buffer(max(n, 1))
+    lib.swb_generate(seed, m, n, a, b)
+    return a.raw[:m], b.raw[:n]
+
+
+def fill_async(a, m: int, b, n: int, dH, dP, pitch: int | None = None, d_maxPos=None, d_maxScore=None,
+               scoring=None, device: int = 0, stream=None, warps_per_band: int = 0, timer=None) -> None:
+    """Enqueue the H/P/maxPos fill; a, b host or device; dH, dP device (n+1)*pitch int32."""
+    sc = _scoring(scoring)
+    tun = Tuning(warps_per_band=warps_per_band, timer=timer._h if timer is not None else None)
+    _check(lib.swb_fill_async(_ptr(a), m, _ptr(b), n, C.byref(sc), _ptr(dH), _ptr(dP), pitch or m + 1,
+                              _ptr(d_maxPos), _ptr(d_maxScore), device, _stream_ptr(stream), C.byref(tun)))
+
+
+def fill(a, m: int, b, n: int, dH, dP, pitch: int | None = None, scoring=None, device: int = 0, stream=None) -> int:
+    """Blocking fill -> maxPos."""
+    sc = _scoring(scoring)
+    pos = C.c_int64(0)
+    _check(lib.swb_fill(_ptr(a), m, _ptr(b), n, C.byref(sc), _ptr(dH), _ptr(dP), pitch or m + 1, C.byref(pos),
+                        device, _stream_ptr(stream)))
+    return int(pos.value)
+
+
+def backtrack(dP, pitch: int, maxPos: int, device: int = 0, stream=None) -> int:
+    """Negates the path in the device P in place -> path length."""
+    n = C.c_int64(0)
+    _check(lib.swb_backtrack(_ptr(dP), pitch, maxPos, C.byref(n), device, _stream_ptr(stream)))
+    return int(n.value)
+
+
+def smithWaterman(a, b, w: int, h: int, H, P, device: int = 0, stream=None, scoring=None) -> int:
+    """Operator of the rotated variants: smithWaterman(a, b, w, h, H, P, &maxloc)
+    (rotated-cuda/sw-rotated-cuda-unified.cu:198-215): a of length w (columns), b of
+    length h (rows), row-major (h+1)*(w+1) outputs that need not be initialised.
+    H, P are DEVICE buffers; returns the offset of the maximum in H (the reference
+    returns a pointer into H)."""
+    return fill(a, w, b, h, H, P, w + 1, scoring=scoring, device=device, stream=stream)
+
+
+def align_host(a: bytes, b: bytes, H=None, P=None, scoring=None, do_backtrack: bool = True, device: int = 0):
+    """Host-buffer call: H2D, fill, backtrack, D2H.  H, P: host int32 buffers of
+    (len(b)+1)*(len(a)+1) (numpy / pinned torch) or None.  -> (maxPos, path_len)"""
+    sc = _scoring(scoring)
+    pos, plen = C.c_int64(0), C.c_int64(0)
+    _check(lib.swb_align_host(_ptr(a), len(a), _ptr(b), len(b), C.byref(sc), _ptr(H), _ptr(P), C.byref(pos),
+                              C.byref(plen), int(do_backtrack), device))
+    return int(pos.value), int(plen.value)
+
+
+class AlignContext:
+    """Keeps the device matrices of one shape alive across host-buffer calls."""
+
+    def __init__(self, m: int, n: int, device: int = 0):
+        self.m, self.n, self.device = m, n, device
+        self._h = C.c_void_p(0)
+        _check(lib.swb_ctx_create(C.byref(self._h), m, n, device))
+
+    def align(self, a, b, H=None, P=None, scoring=None, do_backtrack: bool = True):
+        sc = _scoring(scoring)
+        pos, plen = C.c_int64(0), C.c_int64(0)
+        _check(lib.swb_ctx_align(self._h, _ptr(a), _ptr(b), C.byref(sc), _ptr(H), _ptr(P), C.byref(pos),
+                                 C.byref(plen), int(do_backtrack)))
+        return int(pos.value), int(plen.value)
+
+    @property
+    def dH(self) -> int:
+        return lib.swb_ctx_dH(self._h)
+
+    @property
+    def dP(self) -> int:
+        return lib.swb_ctx_dP(self._h)
+
+    def close(self) -> None:
+        if self._h:
+            lib.swb_ctx_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class KernelTimer:
+    """CUDA-event pair that swb_fill_async records around the fill kernel alone."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p(0)
+        _check(lib.swb_timer_create(C.byref(self._h), device))
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(lib.swb_timer_elapsed_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def close(self) -> None:
+        if self._h:
+            lib.swb_timer_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+
+def score_only(a: bytes, b: bytes, scoring=None, device: int = 0, stream=None):
+    sc = _scoring(scoring)
+    ms, pos = C.c_int32(0), C.c_int64(0)
+    _check(lib.swb_score_only(_ptr(a), len(a), _ptr(b), len(b), C.byref(sc), C.byref(ms), C.byref(pos), device,
+                              _stream_ptr(stream)))
+    return int(ms.value), int(pos.value)
+
+
+def host_alloc(nbytes: int) -> int:
+    p = lib.swb_host_alloc(nbytes)
+    if not p:
+        raise SwbError(f"pinned host allocation of {nbytes} bytes failed")
+    return p
+
+
+def host_free(p: int) -> None:
+    lib.swb_host_free(p)

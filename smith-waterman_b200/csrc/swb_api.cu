@@ -1,0 +1,431 @@
+// swb_api.cu -- thin C ABI over the sm_100a kernels (include/swb200.h).
+// Host code is plain C++/CUDA runtime; no torch types, no CPU fallback.
+#include "../../include/swb200.h"
+#include "swb_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+thread_local char g_cuda_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char* what, int line)
+{
+    std::snprintf(g_cuda_err, sizeof g_cuda_err, "%s failed at swb_api.cu:%d: %s (%s)", what, line,
+                  cudaGetErrorName(e), cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? SWB_ERR_NOMEM : SWB_ERR_CUDA;
+}
+
+#define SWB_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call, __LINE__);         \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1; bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+bool is_device_ptr(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+const swb_scoring kDefaultScoring = {3, -3, -2};     // omp_smithW.c:75-77
+
+int check_scoring(const swb_scoring& sc, int64_t m, int64_t n)
+{
+    const int64_t lim = 1 << 20;
+    if (std::llabs((long long)sc.match) > lim || std::llabs((long long)sc.mismatch) > lim ||
+        std::llabs((long long)sc.gap) > lim)
+        return SWB_ERR_RANGE;
+    // packed keys are 16*H + tie in int32; H <= match * min(m,n)
+    const int64_t hmax = (int64_t)std::max(sc.match, 0) * std::min(m, n);
+    if (hmax >= (1LL << 26)) return SWB_ERR_RANGE;
+    return SWB_OK;
+}
+
+}  // namespace
+struct swb_timer { cudaEvent_t start = nullptr, stop = nullptr; int device = 0; };
+namespace {
+
+struct Workspace {
+    // one stream-ordered allocation, carved up
+    unsigned char* base = nullptr;
+    unsigned* a4 = nullptr; int a4_stride = 0;
+    unsigned char* a_dev = nullptr; unsigned char* b_dev = nullptr;
+    int* ticket = nullptr; int* gmax = nullptr; unsigned long long* key = nullptr;
+    int* progress = nullptr; int nprogress = 0;
+    int* row_max = nullptr;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int pick_wpc(int64_t n, const swb_tuning* tuning)
+{
+    int wpc = 4;
+    if (const char* e = std::getenv("SWB_WPC")) wpc = std::atoi(e);
+    if (tuning && tuning->warps_per_band > 0) wpc = tuning->warps_per_band;
+    wpc = std::max(1, std::min(wpc, swb::kMaxWarps));
+    const int64_t strips = (n + 31) / 32;
+    if (strips < wpc) wpc = (int)strips;
+    return wpc;
+}
+
+template <int MU>
+cudaError_t launch_fill(const swb::FillParams& p, int nbands, int wpc, cudaStream_t st)
+{
+    const size_t smem = (size_t)wpc * swb::kWarpSmemBlocks * sizeof(int4);
+    cudaError_t e = cudaFuncSetAttribute(swb::fill_kernel<MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    swb::fill_kernel<MU><<<nbands, 32 * wpc, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* swb_strerror(int status)
+{
+    switch (status) {
+    case SWB_OK:        return "ok";
+    case SWB_ERR_ARG:   return "invalid argument";
+    case SWB_ERR_ALIGN: return "H/P device buffers must be 16-byte aligned";
+    case SWB_ERR_CUDA:  return "CUDA error (see swb_last_cuda_error)";
+    case SWB_ERR_RANGE: return "sizes or scores exceed the 32-bit packed score range";
+    case SWB_ERR_NOMEM: return "out of device or pinned host memory";
+    default:            return "unknown swb status";
+    }
+}
+
+const char* swb_last_cuda_error(void) { return g_cuda_err; }
+int swb_version(void) { return 100; }
+
+int swb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void swb_generate(unsigned seed, int64_t m, int64_t n, char* a, char* b)
+{
+    // omp_smithW.c:489-519 with the padded loop bounds of :109-110 (m+1 and n+1 draws)
+    auto draw = []() -> char {
+        const int v = rand() % 4;
+        return v == 0 ? 'A' : v == 2 ? 'C' : v == 3 ? 'G' : 'T';
+    };
+    srand(seed);
+    for (int64_t k = 0; k <= m; ++k) { const char c = draw(); if (k < m) a[k] = c; }
+    for (int64_t k = 0; k <= n; ++k) { const char c = draw(); if (k < n) b[k] = c; }
+}
+
+void* swb_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void swb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int swb_timer_create(swb_timer** out, int device)
+{
+    if (!out) return SWB_ERR_ARG;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    swb_timer* t = new swb_timer();
+    t->device = device;
+    cudaError_t e = cudaEventCreate(&t->start);
+    if (e == cudaSuccess) e = cudaEventCreate(&t->stop);
+    if (e != cudaSuccess) { swb_timer_destroy(t); return cuda_fail(e, "cudaEventCreate", __LINE__); }
+    *out = t;
+    return SWB_OK;
+}
+
+int swb_timer_elapsed_ms(swb_timer* t, float* ms)
+{
+    if (!t || !ms) return SWB_ERR_ARG;
+    DeviceGuard guard(t->device);
+    SWB_CUDA(cudaEventSynchronize(t->stop));
+    SWB_CUDA(cudaEventElapsedTime(ms, t->start, t->stop));
+    return SWB_OK;
+}
+
+void swb_timer_destroy(swb_timer* t)
+{
+    if (!t) return;
+    DeviceGuard guard(t->device);
+    if (t->start) cudaEventDestroy(t->start);
+    if (t->stop) cudaEventDestroy(t->stop);
+    delete t;
+}
+
+int swb_fill_async(const char* a, int64_t m, const char* b, int64_t n,
+                   const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch,
+                   int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream,
+                   const swb_tuning* tuning)
+{
+    if (!a || !b || !dH || !dP || m <= 0 || n <= 0 || pitch < m + 1) return SWB_ERR_ARG;
+    if (m >= (1LL << 30) || n >= (1LL << 30)) return SWB_ERR_RANGE;
+    if ((reinterpret_cast<uintptr_t>(dH) & 15) || (reinterpret_cast<uintptr_t>(dP) & 15)) return SWB_ERR_ALIGN;
+    const swb_scoring sc = scoring ? *scoring : kDefaultScoring;
+    if (int rc = check_scoring(sc, m, n)) return rc;
+
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    const int wpc = pick_wpc(n, tuning);
+    const int64_t strips = (n + 31) / 32;
+    const int nbands = (int)((strips + wpc - 1) / wpc);
+    const int qbmax = (int)((m + 3) >> 2) + 1;
+    const int steps = (qbmax + 62 + swb::kGroup - 1) / swb::kGroup * swb::kGroup;
+
+    // ---- workspace (stream ordered)
+    Workspace ws;
+    ws.a4_stride = swb::kAOff + steps + 8;
+    ws.nprogress = nbands + 1;
+    const bool a_on_dev = is_device_ptr(a), b_on_dev = is_device_ptr(b);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_a4 = carve(4ull * ws.a4_stride * sizeof(unsigned));
+    const size_t o_a = carve(a_on_dev ? 0 : (size_t)m);
+    const size_t o_b = carve(b_on_dev ? 0 : (size_t)n);
+    const size_t o_small = carve(256);
+    const size_t o_prog = carve((size_t)ws.nprogress * sizeof(int));
+    const size_t o_rmax = carve((size_t)(n + 1) * sizeof(int));
+    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws.base), off, st));
+    ws.a4 = reinterpret_cast<unsigned*>(ws.base + o_a4);
+    ws.a_dev = ws.base + o_a; ws.b_dev = ws.base + o_b;
+    ws.ticket = reinterpret_cast<int*>(ws.base + o_small);
+    ws.gmax = ws.ticket + 1;
+    ws.key = reinterpret_cast<unsigned long long*>(ws.base + o_small + 16);
+    ws.progress = reinterpret_cast<int*>(ws.base + o_prog);
+    ws.row_max = reinterpret_cast<int*>(ws.base + o_rmax);
+
+    int rc = SWB_OK;
+    auto run = [&]() -> int {
+        const unsigned char* a_d = reinterpret_cast<const unsigned char*>(a);
+        const unsigned char* b_d = reinterpret_cast<const unsigned char*>(b);
+        if (!a_on_dev) { SWB_CUDA(cudaMemcpyAsync(ws.a_dev, a, (size_t)m, cudaMemcpyHostToDevice, st)); a_d = ws.a_dev; }
+        if (!b_on_dev) { SWB_CUDA(cudaMemcpyAsync(ws.b_dev, b, (size_t)n, cudaMemcpyHostToDevice, st)); b_d = ws.b_dev; }
+        // row 0 of H and P (the reference gets it from calloc, omp_smithW.c:113-118)
+        SWB_CUDA(cudaMemsetAsync(dH, 0, (size_t)(m + 1) * sizeof(int32_t), st));
+        SWB_CUDA(cudaMemsetAsync(dP, 0, (size_t)(m + 1) * sizeof(int32_t), st));
+        const int prep_blocks = (int)std::min<int64_t>((4LL * ws.a4_stride + 255) / 256, 1184);
+        swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, ws.a4, ws.a4_stride, ws.progress, ws.nprogress,
+                                                      ws.ticket, ws.gmax, ws.key);
+        SWB_CUDA(cudaGetLastError());
+
+        swb::FillParams p{};
+        p.a4 = ws.a4; p.a4_stride = ws.a4_stride; p.b = b_d;
+        p.H = dH; p.P = dP; p.pitch = pitch; p.m = m; p.n = n;
+        p.s_match = 16 * sc.match + swb::kTieDiag;
+        p.s_mismatch = 16 * sc.mismatch + swb::kTieDiag;
+        p.g_up = 16 * sc.gap + swb::kTieUp;
+        p.g_left = 16 * sc.gap + swb::kTieLeft;
+        p.steps = steps; p.qbmax = qbmax;
+        p.ticket = ws.ticket; p.progress = ws.progress; p.row_max = ws.row_max; p.gmax = ws.gmax;
+        cudaError_t e;
+        swb_timer* timer = tuning ? tuning->timer : nullptr;
+        if (timer) SWB_CUDA(cudaEventRecord(timer->start, st));
+        switch ((int)(pitch & 3)) {
+        case 0:  e = launch_fill<0>(p, nbands, wpc, st); break;
+        case 1:  e = launch_fill<1>(p, nbands, wpc, st); break;
+        case 2:  e = launch_fill<2>(p, nbands, wpc, st); break;
+        default: e = launch_fill<3>(p, nbands, wpc, st); break;
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "fill_kernel launch", __LINE__);
+        if (timer) SWB_CUDA(cudaEventRecord(timer->stop, st));
+
+        const int am_blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
+        swb::argmax_kernel<<<am_blocks, 256, 0, st>>>(dH, pitch, m, n, ws.row_max, ws.gmax, ws.key);
+        SWB_CUDA(cudaGetLastError());
+        swb::finalize_kernel<<<1, 1, 0, st>>>(ws.key, ws.gmax, pitch, reinterpret_cast<long long*>(d_maxPos), d_maxScore);
+        SWB_CUDA(cudaGetLastError());
+        return SWB_OK;
+    };
+    rc = run();
+    cudaError_t fe = cudaFreeAsync(ws.base, st);
+    if (rc == SWB_OK && fe != cudaSuccess) rc = cuda_fail(fe, "cudaFreeAsync", __LINE__);
+    return rc;
+}
+
+int swb_fill(const char* a, int64_t m, const char* b, int64_t n,
+             const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch,
+             int64_t* maxPos, int device, void* stream)
+{
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    long long* d_pos = nullptr;
+    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_pos), sizeof(long long), st));
+    int rc = swb_fill_async(a, m, b, n, scoring, dH, dP, pitch, reinterpret_cast<int64_t*>(d_pos), nullptr,
+                            device, stream, nullptr);
+    long long pos = 0;
+    if (rc == SWB_OK) {
+        cudaError_t e = cudaMemcpyAsync(&pos, d_pos, sizeof pos, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "maxPos readback", __LINE__);
+    }
+    cudaFreeAsync(d_pos, st);
+    if (rc == SWB_OK && maxPos) *maxPos = pos;
+    return rc;
+}
+
+int swb_backtrack_async(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_t* d_maxPos,
+                        int64_t* d_pathLen, int device, void* stream)
+{
+    if (!dP || pitch <= 1 || (!d_maxPos && maxPos < 0)) return SWB_ERR_ARG;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    swb::backtrack_kernel<<<1, 32, 0, st>>>(dP, pitch, maxPos, reinterpret_cast<const long long*>(d_maxPos),
+                                            reinterpret_cast<long long*>(d_pathLen));
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+
+int swb_backtrack(int32_t* dP, int64_t pitch, int64_t maxPos, int64_t* path_len, int device, void* stream)
+{
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    long long* d_len = nullptr;
+    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_len), sizeof(long long), st));
+    int rc = swb_backtrack_async(dP, pitch, maxPos, nullptr, reinterpret_cast<int64_t*>(d_len), device, stream);
+    long long len = 0;
+    if (rc == SWB_OK) {
+        cudaError_t e = cudaMemcpyAsync(&len, d_len, sizeof len, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "path length readback", __LINE__);
+    }
+    cudaFreeAsync(d_len, st);
+    if (rc == SWB_OK && path_len) *path_len = len;
+    return rc;
+}
+
+// ------------------------------------------------------------------ host-buffer API
+struct swb_ctx {
+    int device = 0;
+    int64_t m = 0, n = 0;
+    int32_t* dH = nullptr; int32_t* dP = nullptr;
+    long long* d_scalars = nullptr;        // [0] maxPos, [1] pathLen
+    cudaStream_t st = nullptr;
+};
+
+int swb_ctx_create(swb_ctx** out, int64_t m, int64_t n, int device)
+{
+    if (!out || m <= 0 || n <= 0) return SWB_ERR_ARG;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    swb_ctx* c = new swb_ctx();
+    c->device = device; c->m = m; c->n = n;
+    const size_t bytes = (size_t)(m + 1) * (size_t)(n + 1) * sizeof(int32_t);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->dH), bytes);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->dP), bytes);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_scalars), 2 * sizeof(long long));
+    if (e != cudaSuccess) { int rc = cuda_fail(e, "swb_ctx_create allocation", __LINE__); swb_ctx_destroy(c); return rc; }
+    *out = c;
+    return SWB_OK;
+}
+
+void swb_ctx_destroy(swb_ctx* c)
+{
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    if (c->dH) cudaFree(c->dH);
+    if (c->dP) cudaFree(c->dP);
+    if (c->d_scalars) cudaFree(c->d_scalars);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+int32_t* swb_ctx_dH(swb_ctx* c) { return c ? c->dH : nullptr; }
+int32_t* swb_ctx_dP(swb_ctx* c) { return c ? c->dP : nullptr; }
+
+int swb_ctx_align(swb_ctx* c, const char* a, const char* b, const swb_scoring* scoring,
+                  int32_t* H, int32_t* P, int64_t* maxPos, int64_t* path_len, int do_backtrack)
+{
+    if (!c || !a || !b) return SWB_ERR_ARG;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    const size_t bytes = (size_t)(c->m + 1) * (size_t)(c->n + 1) * sizeof(int32_t);
+    int rc = swb_fill_async(a, c->m, b, c->n, scoring, c->dH, c->dP, c->m + 1,
+                            reinterpret_cast<int64_t*>(c->d_scalars), nullptr, c->device, c->st, nullptr);
+    if (rc != SWB_OK) return rc;
+    // H does not change any more: start its copy-back before the backtrack
+    if (H) SWB_CUDA(cudaMemcpyAsync(H, c->dH, bytes, cudaMemcpyDeviceToHost, c->st));
+    if (do_backtrack) {
+        rc = swb_backtrack_async(c->dP, c->m + 1, 0, reinterpret_cast<int64_t*>(c->d_scalars),
+                                 reinterpret_cast<int64_t*>(c->d_scalars + 1), c->device, c->st);
+        if (rc != SWB_OK) return rc;
+    } else {
+        SWB_CUDA(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(long long), c->st));
+    }
+    if (P) SWB_CUDA(cudaMemcpyAsync(P, c->dP, bytes, cudaMemcpyDeviceToHost, c->st));
+    long long sc2[2] = {0, 0};
+    SWB_CUDA(cudaMemcpyAsync(sc2, c->d_scalars, sizeof sc2, cudaMemcpyDeviceToHost, c->st));
+    SWB_CUDA(cudaStreamSynchronize(c->st));
+    if (maxPos) *maxPos = sc2[0];
+    if (path_len) *path_len = sc2[1];
+    return SWB_OK;
+}
+
+int swb_align_host(const char* a, int64_t m, const char* b, int64_t n,
+                   const swb_scoring* scoring, int32_t* H, int32_t* P,
+                   int64_t* maxPos, int64_t* path_len, int do_backtrack, int device)
+{
+    swb_ctx* c = nullptr;
+    int rc = swb_ctx_create(&c, m, n, device);
+    if (rc != SWB_OK) return rc;
+    rc = swb_ctx_align(c, a, b, scoring, H, P, maxPos, path_len, do_backtrack);
+    swb_ctx_destroy(c);
+    return rc;
+}
+
+int swb_score_only(const char* a, int64_t m, const char* b, int64_t n,
+                   const swb_scoring* scoring, int32_t* maxScore, int64_t* maxPos,
+                   int device, void* stream)
+{
+    // PROVISIONAL (round 1): runs the full fill into temporary matrices and drops them.
+    // The dedicated no-store kernel replaces this.
+    if (m <= 0 || n <= 0) return SWB_ERR_ARG;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)(m + 1) * (size_t)(n + 1) * sizeof(int32_t);
+    int32_t *dH = nullptr, *dP = nullptr; long long* d_pos = nullptr; int32_t* d_sc = nullptr;
+    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dH), bytes, st));
+    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dP), bytes, st));
+    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_pos), 16, st));
+    d_sc = reinterpret_cast<int32_t*>(d_pos + 1);
+    int rc = swb_fill_async(a, m, b, n, scoring, dH, dP, m + 1, reinterpret_cast<int64_t*>(d_pos), d_sc, device, stream, nullptr);
+    long long host[2] = {0, 0};
+    if (rc == SWB_OK) {
+        cudaError_t e = cudaMemcpyAsync(host, d_pos, 16, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "score readback", __LINE__);
+    }
+    cudaFreeAsync(dH, st); cudaFreeAsync(dP, st); cudaFreeAsync(d_pos, st);
+    if (rc == SWB_OK) {
+        if (maxPos) *maxPos = host[0];
+        if (maxScore) *maxScore = (int32_t)(host[1] & 0xffffffff);
+    }
+    return rc;
+}
+
+}  // extern "C"

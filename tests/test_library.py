@@ -1,0 +1,72 @@
+"""CPU-side checks of the product boundary: the C-ABI library builds/loads and exports
+every symbol include/swb200.h declares; the schedule model of the kernel reproduces the
+oracle; host-side helpers agree with the reference's generate().  No compute calls."""
+import ctypes
+import re
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "swb200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(swb_[A-Za-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(swb):
+    names = declared_symbols()
+    assert len(names) >= 18
+    lib = ctypes.CDLL(str(swb.LIB_PATH))
+    for nm in names:
+        assert hasattr(lib, nm), f"{nm} declared in include/swb200.h but not exported"
+    assert swb.lib.swb_version() >= 100
+    assert swb.lib.swb_strerror(-2).decode().startswith("H/P")
+
+
+def test_library_is_sm100a_only(swb):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", str(swb.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_generate_matches_reference_generator(swb, oracle, golden_dir):
+    z = np.load(golden_dir / "ref_small.npz")
+    for t in sorted({k.split("_")[0] for k in z.files}):
+        cols, rows, seed = (int(x) for x in z[f"{t}_meta"][:3])
+        if cols <= 0:
+            continue
+        a, b = swb.generate(seed, cols, rows)
+        assert a == bytes(z[f"{t}_a"]) and b == bytes(z[f"{t}_b"])
+
+
+def test_no_gpu_means_loud_failure(swb):
+    if swb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(swb.SwbError):
+        swb.align_host(b"ACGT", b"ACG", None, None)
+
+
+def test_product_never_touches_the_oracle():
+    for p in (ROOT / "smith-waterman_b200").rglob("*"):
+        if p.suffix in {".py", ".cu", ".cuh", ".cpp", ".h"} or p.name == "Makefile":
+            txt = p.read_text()
+            assert "oracle" not in txt.replace("the oracle", "").lower() or "sw_oracle" not in txt, p
+            assert "sw_oracle" not in txt and "libsworacle" not in txt and "swo_" not in txt, p
+
+
+@pytest.mark.parametrize("m,n,wpc", [(8, 9, 4), (130, 33, 1), (131, 64, 4), (132, 65, 2), (133, 100, 4), (303, 70, 3)])
+def test_schedule_model_reproduces_oracle(oracle, m, n, wpc):
+    from schedule_model import fill_model
+    rng = np.random.default_rng(m * 1000 + n)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    a, b = rng.choice(acgt, m), rng.choice(acgt, n)
+    H, P, _ = oracle.fill(a, b)
+    Hm, Pm, rmax = fill_model(a, b, wpc=wpc)
+    assert (Hm == H).all() and (Pm == P).all() and (rmax[1:] == H[1:].max(axis=1)).all()
