@@ -17,7 +17,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-__all__ = ["lib", "SwbError", "Scoring", "DEFAULT_SCORING", "generate", "fill", "fill_async", "backtrack",
+__all__ = ["lib", "SwbError", "Scoring", "DEFAULT_SCORING", "generate", "fill", "fill_async", "backtrack", "backtrack_async",
            "smithWaterman", "align_host", "AlignContext", "score_only", "KernelTimer", "host_alloc", "host_free",
            "device_count", "LIB_PATH", "NONE", "UP", "LEFT", "DIAGONAL", "PATH"]
 
@@ -150,6 +150,13 @@ def backtrack(dP, pitch: int, maxPos: int, device: int = 0, stream=None) -> int:
     n = C.c_int64(0)
     _check(lib.swb_backtrack(_ptr(dP), pitch, maxPos, C.byref(n), device, _stream_ptr(stream)))
     return int(n.value)
+
+
+def backtrack_async(dP, pitch: int, maxPos: int = 0, d_maxPos=None, d_pathLen=None, device: int = 0,
+                    stream=None) -> None:
+    """Enqueue the backtrack; d_maxPos (device int64, e.g. fill_async's output) takes precedence over maxPos."""
+    _check(lib.swb_backtrack_async(_ptr(dP), pitch, maxPos, _ptr(d_maxPos), _ptr(d_pathLen), device,
+                                   _stream_ptr(stream)))
 
 
 def smithWaterman(a, b, w: int, h: int, H, P, device: int = 0, stream=None, scoring=None) -> int:
