@@ -56,9 +56,10 @@ typedef struct { int32_t match, mismatch, gap; } swb_scoring;
 /* Tuning knobs (0 = library default).  Not part of the reference surface. */
 typedef struct swb_timer swb_timer;   /* CUDA-event pair around the fill kernel only */
 typedef struct {
-    int32_t warps_per_band;   /* warps (32-row strips) per CTA band, 1..16          */
+    int32_t warps_per_band;   /* compute warps (32-row strips) per CTA band, 1..4   */
     int32_t reserved[5];
     swb_timer* timer;         /* if set, swb_fill_async brackets the fill kernel launch with its events */
+    uint64_t* trace;          /* developer tool: DEVICE buffer of ceil(n/32)*8 uint64 globaltimer stamps per strip, or NULL */
 } swb_tuning;
 
 /* Kernel-only timing for the roofline figure: events are recorded on the call's stream

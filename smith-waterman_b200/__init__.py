@@ -24,7 +24,7 @@ __all__ = ["lib", "SwbError", "Scoring", "DEFAULT_SCORING", "generate", "fill", 
 # omp_smithW.c:32-36
 PATH, NONE, UP, LEFT, DIAGONAL = -1, 0, 1, 2, 3
 
-LIB_PATH = Path(__file__).resolve().parent / "libswb200.so"
+LIB_PATH = Path(os.environ.get("SWB_LIB", Path(__file__).resolve().parent / "libswb200.so"))
 
 
 class SwbError(RuntimeError):
@@ -37,7 +37,8 @@ class Scoring(C.Structure):
 
 
 class Tuning(C.Structure):
-    _fields_ = [("warps_per_band", C.c_int32), ("reserved", C.c_int32 * 5), ("timer", C.c_void_p)]
+    _fields_ = [("warps_per_band", C.c_int32), ("reserved", C.c_int32 * 5), ("timer", C.c_void_p),
+                ("trace", C.c_void_p)]
 
 
 DEFAULT_SCORING = (3, -3, -2)
@@ -128,10 +129,11 @@ def generate(seed: int, m: int, n: int):
 
 
 def fill_async(a, m: int, b, n: int, dH, dP, pitch: int | None = None, d_maxPos=None, d_maxScore=None,
-               scoring=None, device: int = 0, stream=None, warps_per_band: int = 0, timer=None) -> None:
+               scoring=None, device: int = 0, stream=None, warps_per_band: int = 0, timer=None, trace=None) -> None:
     """Enqueue the H/P/maxPos fill; a, b host or device; dH, dP device (n+1)*pitch int32."""
     sc = _scoring(scoring)
-    tun = Tuning(warps_per_band=warps_per_band, timer=timer._h if timer is not None else None)
+    tun = Tuning(warps_per_band=warps_per_band, timer=timer._h if timer is not None else None,
+                 trace=_ptr(trace) if trace is not None else None)
     _check(lib.swb_fill_async(_ptr(a), m, _ptr(b), n, C.byref(sc), _ptr(dH), _ptr(dP), pitch or m + 1,
                               _ptr(d_maxPos), _ptr(d_maxScore), device, _stream_ptr(stream), C.byref(tun)))
 

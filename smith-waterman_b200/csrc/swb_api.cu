@@ -63,34 +63,30 @@ namespace {
 struct Workspace {
     // one stream-ordered allocation, carved up
     unsigned char* base = nullptr;
-    unsigned* a4 = nullptr; int a4_stride = 0;
+    unsigned* a4 = nullptr; long long a4_words = 0;
     unsigned char* a_dev = nullptr; unsigned char* b_dev = nullptr;
     int* ticket = nullptr; int* gmax = nullptr; unsigned long long* key = nullptr;
-    int* progress = nullptr; int nprogress = 0;
-    int* row_max = nullptr;
+    int* strip_max = nullptr;
+    int4* boundary = nullptr; long long bstride = 0;
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int pick_wpc(int64_t n, const swb_tuning* tuning)
 {
-    int wpc = 4;
+    int wpc = 2;
     if (const char* e = std::getenv("SWB_WPC")) wpc = std::atoi(e);
     if (tuning && tuning->warps_per_band > 0) wpc = tuning->warps_per_band;
-    wpc = std::max(1, std::min(wpc, swb::kMaxWarps));
+    wpc = std::max(1, std::min(wpc, swb::kMaxWpc));
     const int64_t strips = (n + 31) / 32;
     if (strips < wpc) wpc = (int)strips;
     return wpc;
 }
 
-template <int MU>
-cudaError_t launch_fill(const swb::FillParams& p, int nbands, int wpc, cudaStream_t st)
+size_t fill_smem_bytes(int wpc)
 {
-    const size_t smem = (size_t)wpc * swb::kWarpSmemBlocks * sizeof(int4);
-    cudaError_t e = cudaFuncSetAttribute(swb::fill_kernel<MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    swb::fill_kernel<MU><<<nbands, 32 * wpc, smem, st>>>(p);
-    return cudaGetLastError();
+    return (size_t)wpc * (32 * swb::kRowInts * sizeof(int) + swb::kRing * sizeof(int4) + 32 * sizeof(int4) +
+                          64 * sizeof(int));
 }
 
 }  // namespace
@@ -190,30 +186,31 @@ int swb_fill_async(const char* a, int64_t m, const char* b, int64_t n,
     const int wpc = pick_wpc(n, tuning);
     const int64_t strips = (n + 31) / 32;
     const int nbands = (int)((strips + wpc - 1) / wpc);
-    const int qbmax = (int)((m + 3) >> 2) + 1;
-    const int steps = (qbmax + 62 + swb::kGroup - 1) / swb::kGroup * swb::kGroup;
+    const int jmax = (int)(m >> 2);                                   // last block with a valid column
+    const int ngroups = (jmax + 1 + 31 + swb::kGroup - 1) / swb::kGroup;
 
     // ---- workspace (stream ordered)
     Workspace ws;
-    ws.a4_stride = swb::kAOff + steps + 8;
-    ws.nprogress = nbands + 1;
+    ws.a4_words = swb::kAPad + (long long)ngroups * swb::kGroup + 16;
+    ws.bstride = (long long)ngroups * swb::kGroup;
     const bool a_on_dev = is_device_ptr(a), b_on_dev = is_device_ptr(b);
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_a4 = carve(4ull * ws.a4_stride * sizeof(unsigned));
+    const size_t o_a4 = carve((size_t)ws.a4_words * sizeof(unsigned));
     const size_t o_a = carve(a_on_dev ? 0 : (size_t)m);
     const size_t o_b = carve(b_on_dev ? 0 : (size_t)n);
     const size_t o_small = carve(256);
-    const size_t o_prog = carve((size_t)ws.nprogress * sizeof(int));
-    const size_t o_rmax = carve((size_t)(n + 1) * sizeof(int));
+    const size_t o_smax = carve((size_t)strips * sizeof(int));
+    const size_t boundary_bytes = (size_t)std::max(nbands - 1, 0) * (size_t)ws.bstride * sizeof(int4);
+    const size_t o_bnd = carve(boundary_bytes);
     SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws.base), off, st));
     ws.a4 = reinterpret_cast<unsigned*>(ws.base + o_a4);
     ws.a_dev = ws.base + o_a; ws.b_dev = ws.base + o_b;
     ws.ticket = reinterpret_cast<int*>(ws.base + o_small);
     ws.gmax = ws.ticket + 1;
     ws.key = reinterpret_cast<unsigned long long*>(ws.base + o_small + 16);
-    ws.progress = reinterpret_cast<int*>(ws.base + o_prog);
-    ws.row_max = reinterpret_cast<int*>(ws.base + o_rmax);
+    ws.strip_max = reinterpret_cast<int*>(ws.base + o_smax);
+    ws.boundary = reinterpret_cast<int4*>(ws.base + o_bnd);
 
     int rc = SWB_OK;
     auto run = [&]() -> int {
@@ -224,34 +221,34 @@ int swb_fill_async(const char* a, int64_t m, const char* b, int64_t n,
         // row 0 of H and P (the reference gets it from calloc, omp_smithW.c:113-118)
         SWB_CUDA(cudaMemsetAsync(dH, 0, (size_t)(m + 1) * sizeof(int32_t), st));
         SWB_CUDA(cudaMemsetAsync(dP, 0, (size_t)(m + 1) * sizeof(int32_t), st));
-        const int prep_blocks = (int)std::min<int64_t>((4LL * ws.a4_stride + 255) / 256, 1184);
-        swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, ws.a4, ws.a4_stride, ws.progress, ws.nprogress,
-                                                      ws.ticket, ws.gmax, ws.key);
+        // band-boundary rows carry their validity tag in the data: clear the tags
+        if (boundary_bytes) SWB_CUDA(cudaMemsetAsync(ws.boundary, 0, boundary_bytes, st));
+        const int prep_blocks = (int)std::min<int64_t>((ws.a4_words + 255) / 256, 1184);
+        swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, ws.a4, ws.a4_words, ws.ticket, ws.gmax, ws.key);
         SWB_CUDA(cudaGetLastError());
 
         swb::FillParams p{};
-        p.a4 = ws.a4; p.a4_stride = ws.a4_stride; p.b = b_d;
+        p.a4 = ws.a4; p.b = b_d;
         p.H = dH; p.P = dP; p.pitch = pitch; p.m = m; p.n = n;
         p.s_match = 16 * sc.match + swb::kTieDiag;
         p.s_mismatch = 16 * sc.mismatch + swb::kTieDiag;
         p.g_up = 16 * sc.gap + swb::kTieUp;
         p.g_left = 16 * sc.gap + swb::kTieLeft;
-        p.steps = steps; p.qbmax = qbmax;
-        p.ticket = ws.ticket; p.progress = ws.progress; p.row_max = ws.row_max; p.gmax = ws.gmax;
-        cudaError_t e;
+        p.ngroups = ngroups; p.jmax = jmax; p.wpc = wpc;
+        p.boundary = ws.boundary; p.bstride = ws.bstride;
+        p.ticket = ws.ticket; p.strip_max = ws.strip_max; p.gmax = ws.gmax;
+        p.trace = tuning ? reinterpret_cast<unsigned long long*>(tuning->trace) : nullptr;
+        const size_t smem = fill_smem_bytes(wpc);
+        SWB_CUDA(cudaFuncSetAttribute(swb::fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)fill_smem_bytes(swb::kMaxWpc)));
         swb_timer* timer = tuning ? tuning->timer : nullptr;
         if (timer) SWB_CUDA(cudaEventRecord(timer->start, st));
-        switch ((int)(pitch & 3)) {
-        case 0:  e = launch_fill<0>(p, nbands, wpc, st); break;
-        case 1:  e = launch_fill<1>(p, nbands, wpc, st); break;
-        case 2:  e = launch_fill<2>(p, nbands, wpc, st); break;
-        default: e = launch_fill<3>(p, nbands, wpc, st); break;
-        }
-        if (e != cudaSuccess) return cuda_fail(e, "fill_kernel launch", __LINE__);
+        swb::fill_kernel<<<nbands, 32 * (2 * wpc + 1), smem, st>>>(p);
+        SWB_CUDA(cudaGetLastError());
         if (timer) SWB_CUDA(cudaEventRecord(timer->stop, st));
 
         const int am_blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
-        swb::argmax_kernel<<<am_blocks, 256, 0, st>>>(dH, pitch, m, n, ws.row_max, ws.gmax, ws.key);
+        swb::argmax_kernel<<<am_blocks, 256, 0, st>>>(dH, pitch, m, n, ws.strip_max, ws.gmax, ws.key);
         SWB_CUDA(cudaGetLastError());
         swb::finalize_kernel<<<1, 1, 0, st>>>(ws.key, ws.gmax, pitch, reinterpret_cast<long long*>(d_maxPos), d_maxScore);
         SWB_CUDA(cudaGetLastError());

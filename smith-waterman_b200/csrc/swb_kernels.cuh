@@ -1,56 +1,58 @@
 // swb_kernels.cuh -- sm_100a kernels of the Smith-Waterman fill / backtrack path.
 //
 // Replaces the nDiag wavefront loop + similarityScore + backtrack of the reference
-// (omp_smithW.c:203-216, 331-388, 405-420).  See DESIGN.md for the derivation; the
-// short version:
+// (omp_smithW.c:203-216, 331-388, 405-420).  DESIGN.md has the derivation and the
+// measurements; the short version of the fill kernel:
 //
-//  * The matrix is cut into horizontal STRIPS of 32 rows.  One warp owns a strip and
-//    sweeps it left to right; lane l owns row r0+l.  Per STEP every lane computes one
-//    16-byte BLOCK (4 consecutive columns) of its row, so H never leaves registers on
-//    the dependency chain: the block of the row above arrives by __shfl_up_sync.
-//  * pitch = m+1 is in general not a multiple of 4, so "4 consecutive columns" is
-//    chosen PER ROW such that every block is a 16-byte aligned int4 of the caller's
-//    row-major H/P:  row r has phase phi_r = (r*pitch)&3 and its block qb covers
-//    columns 4*qb - phi_r .. +3.  Consecutive rows differ by MU = pitch&3 columns of
-//    phase; lane l lags lane l-1 by one step plus that phase (sigma_l extra steps
-//    accumulated), and the two most recent blocks of the upper row (8 registers) always
-//    contain the 5 upper/diagonal values a block needs -- at compile-time positions
-//    (template parameter MU).
-//  * A cell is computed on packed keys K = 16*H + tie, tie in {NONE 8, DIAG 7, UP 5,
-//    LEFT 2}: one max over the four candidates reproduces the reference's strict-'>'
-//    order DIAGONAL, UP, LEFT (omp_smithW.c:348-378), and P = K&3, H = K>>4.  Three
-//    DPX VIADDMNMX per cell.
-//  * Finished blocks go to a per-warp shared-memory staging ring; whenever a row has 8
-//    blocks (128 contiguous bytes) eight lanes write them out with 16-byte stores, so
-//    every global store instruction writes four full 128-byte row segments.
-//  * Strip -> strip hand-off (row 32 of a strip feeds row 1 of the next):  inside a CTA
-//    ("band" of wpc strips) through a shared-memory ring + progress counters, between
-//    bands through H itself in global/L2 + a device-scope progress flag (release /
-//    acquire).  Bands are claimed from an atomic ticket in start order, so a waiting
-//    band's predecessor is always resident: the whole fill is ONE launch, anti-
-//    diagonals are not launches.
-//  * Per-row maxima fall out of the lane registers; a second tiny kernel scans only the
-//    rows that attain the global maximum to find maxPos with the reference's tie-break
-//    (first in anti-diagonal order, bottom-left to top-right; omp_smithW.c:203-215,384-387).
+//  * The matrix is cut into STRIPS of 32 rows.  A COMPUTE warp owns a strip and sweeps it
+//    left to right: lane l owns row r0+l and computes, per STEP t, the BLOCK j = t-l of four
+//    columns 4j..4j+3 (column 0 is the zero boundary column and is computed like any other).
+//    H stays in registers on the dependency chain: the block of the row above arrives by
+//    __shfl_up_sync, the cell to the left is the lane's own previous value.
+//  * A cell is computed on packed keys K = 16*H + tie, tie in {NONE 8, DIAG 7, UP 5, LEFT 2}:
+//    one max over the four candidates reproduces the reference's strict-'>' order
+//    DIAGONAL, UP, LEFT (omp_smithW.c:348-378); P = K&3, H = K>>4.  Three DPX VIADDMNMX per
+//    cell, of which one is on the chain.
+//  * Warp specialisation.  The compute warp only stages its packed block (one 16-byte
+//    STS per lane per step) in a shared-memory ring.  A WRITER warp per strip drains the
+//    ring: for every row it reads 32 consecutive columns (conflict-free LDS.32), unpacks H
+//    and P and stores them with two warp-wide stores that each cover ONE FULL 128-byte
+//    line of the caller's row-major matrix (the segmentation is chosen per row so that
+//    this holds for any pitch).  The writer also keeps the strip maximum for maxPos.
+//  * Strip -> strip hand-off (row 32 of a strip feeds row 1 of the next): lane 31 stores
+//    its H block into a 64-entry shared-memory ring of the next compute warp of the CTA
+//    ("band" = wpc strips); the entry carries an epoch tag in its low bits, so the
+//    consumer polls the DATA and no fence sits on the dependency chain.  Band -> band goes
+//    through a tagged boundary row in global memory (L2) that a LOADER warp of the next
+//    band copies into that band's first ring.  Bands are claimed from an atomic ticket in
+//    start order, so a waiting band's predecessor is always resident: the whole fill is
+//    ONE launch, anti-diagonals are not launches.
+//  * maxPos: a second tiny kernel scans only the strips that attain the global maximum,
+//    with the reference's tie-break (first in anti-diagonal order, bottom-left to
+//    top-right; omp_smithW.c:203-215,384-387).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace swb {
 
-constexpr int kRingBlocks = 64;     // hand-off ring capacity in 16-byte blocks (power of two)
-constexpr int kGroup      = 8;      // steps per synchronisation group == staging ring depth
-constexpr int kAOff       = 64;     // leading pad words of the shifted copies of a
-constexpr int kMaxWarps   = 16;     // strips per band (CTA) upper bound
-constexpr int kWarpSmemBlocks = 32 * kGroup + kRingBlocks;   // int4 per warp
+constexpr int kT        = 64;          // staging ring depth in steps (16-byte slots per row)
+constexpr int kRowInts  = 4 * kT;      // ints per row of the staging ring
+constexpr int kRing     = 64;          // hand-off ring capacity in blocks (power of two)
+constexpr int kGroup    = 8;           // steps per synchronisation group
+constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
+constexpr int kMaxWpc   = 4;           // strips per band (CTA) upper bound
+constexpr int kDrainRounds = 2;        // writer rounds after the last compute group
+// writer round r reads steps [8r-8, 8r+7]; compute group g overwrites the slots of group
+// g - kT/8, which rounds <= g - kT/8 + 1 read: g may start once that many rounds are done
+constexpr int kStageSlack = kT / kGroup - 2;
 
 // tie codes: larger wins on equal score => NONE > DIAGONAL > UP > LEFT, and code&3 is
 // the reference's P value (omp_smithW.c:33-36)
 constexpr int kTieNone = 8, kTieDiag = 7, kTieUp = 5, kTieLeft = 2;
 
 struct FillParams {
-    const unsigned* a4;      // 4 phase-shifted word copies of a (built by prep_kernel)
-    int             a4_stride;
+    const unsigned* a4;      // a4[kAPad + j] = a[4j-1 .. 4j+2] (block j; 0 outside [0,m))
     const unsigned char* b;  // n bytes, device
     int32_t*        H;
     int32_t*        P;
@@ -58,24 +60,26 @@ struct FillParams {
     long long       m, n;
     int             s_match, s_mismatch;   // 16*score + kTieDiag
     int             g_up, g_left;          // 16*gap + kTieUp / kTieLeft
-    int             steps;                 // steps per strip, multiple of kGroup
-    int             qbmax;                 // blocks that can hold valid columns: ((m+3)>>2)+1
+    int             ngroups;               // compute groups per strip
+    int             jmax;                  // last block holding a valid column: m >> 2
+    int             wpc;                   // compute warps (strips) per band
+    int4*           boundary;              // [nbands][bstride] tagged blocks: last row of band k
+    long long       bstride;
     int*            ticket;                // band ticket counter
-    int*            progress;              // [nbands+1]; [k+1] = blocks of band k's last row visible in H
-    int*            row_max;               // [n+1] max H of each row
+    int*            strip_max;             // [nstrips] max H of each strip
     int*            gmax;                  // global max H
+    unsigned long long* trace;             // optional [nstrips][8] globaltimer stamps (developer tool) or nullptr
 };
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p)
+__device__ __forceinline__ void trace_stamp(const FillParams& p, long long strip, int slot, int lane)
 {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+    if (p.trace && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[strip * 8 + slot] = t;
+    }
 }
-__device__ __forceinline__ void st_release_gpu(int* p, int v)
-{
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+
 __device__ __forceinline__ int4 ld_cg_int4(const int4* p)
 {
     int4 v;
@@ -83,31 +87,56 @@ __device__ __forceinline__ int4 ld_cg_int4(const int4* p)
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_cs_int4(int4* p, const int4& v)
+__device__ __forceinline__ void st_cg_int4(int4* p, const int4& v)
 {
-    asm volatile("st.global.cs.v4.s32 [%0], {%1,%2,%3,%4};"
+    asm volatile("st.global.cg.v4.s32 [%0], {%1,%2,%3,%4};"
                  ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cs_int(int32_t* p, int v)
+{
+    asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int4 lds_volatile_int4(const int4* p)
+{
+    int4 v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile_int4(int4* p, const int4& v)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4};"
+                 ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// stores under a PTX predicate: no branch, so a compute warp cannot diverge here
+__device__ __forceinline__ void sts_volatile_int4_if(int4* p, const int4& v, bool on)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4}; }"
+                 ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((unsigned)on) : "memory");
+}
+__device__ __forceinline__ void st_cg_int4_if(int4* p, const int4& v, bool on)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.global.cg.v4.s32 [%0], {%1,%2,%3,%4}; }"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((unsigned)on) : "memory");
 }
 
 // ---------------------------------------------------------------------------------
-// prep: 4 byte-shifted word copies of a, so that a lane whose blocks start at
-// columns == -phi (mod 4) reads the 4 characters of a block with ONE aligned 32-bit load.
-//   copy s, word kAOff+qb, byte e  =  a[4*qb + s + e - 4]      (0 outside [0,m))
-// A lane of phase phi uses copy s = 3-phi: byte e of word qb is a[col-1] for
-// col = 4*qb - phi + e   (matchMissmatchScore reads a[j-1], omp_smithW.c:395).
-// Also arms the workspace words.
+// prep: packed copy of a -- word kAPad+j holds the characters of block j (columns
+// 4j..4j+3; column c reads a[c-1], omp_smithW.c:395), zero outside the sequence --
+// and arms the workspace words.
 // ---------------------------------------------------------------------------------
 __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m,
-                            unsigned* __restrict__ a4, int stride,
-                            int* progress, int nprogress, int* ticket, int* gmax,
-                            unsigned long long* key)
+                            unsigned* __restrict__ a4, long long nwords,
+                            int* ticket, int* gmax, unsigned long long* key)
 {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
-    for (long long w = tid; w < 4LL * stride; w += nth) {
-        const int s = (int)(w / stride);
-        const long long k = w % stride;
-        const long long base = 4 * (k - kAOff) + s - 4;
+    for (long long w = tid; w < nwords; w += nth) {
+        const long long base = 4 * (w - kAPad) - 1;
         unsigned word = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -117,266 +146,399 @@ __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m,
         }
         a4[w] = word;
     }
-    for (long long k = tid; k < nprogress; k += nth) progress[k] = (k == 0) ? 0x7fffffff : 0;
     if (tid == 0) { *ticket = 0; *gmax = 0; *key = ~0ull; }
 }
 
 // ---------------------------------------------------------------------------------
-// The fill kernel.  grid = number of bands, block = 32*wpc threads,
-// dynamic smem = wpc * kWarpSmemBlocks * 16 bytes.
+// compute warp
 // ---------------------------------------------------------------------------------
-template <int MU>
+#ifndef SWB_X_GATESLEEP
+#define SWB_X_GATESLEEP 100
+#endif
+
+// ---------------------------------------------------------------------------------
+// compute warp.  IMPORTANT: a compute warp never diverges -- every poll loop is executed
+// by all 32 lanes on a broadcast address.  (A lane-0-only spin loop leaves the warp split
+// and every following shuffle takes the divergent slow path: measured 8x slower steps.)
+// ---------------------------------------------------------------------------------
 struct Strip {
-    // ---- per-lane constants
-    int lane, cbase;              // first column of the block of step t is 4*t + cbase
+    int lane;
     unsigned b4;
-    const unsigned* aw;           // aw[t] = the 4 characters of the block of step t
     int sm, sx, gu, gl;
-    int m;
-    // ---- dependency state (registers)
-    int A[4], B[4];               // the two most recent blocks of the row above (clean 16*H)
-    int hl;                       // clean 16*H of the last cell of my previous block
-    int rmax;                     // running max of K over my row
-    unsigned aword;
-    // ---- shared memory
-    int4* stage;                  // [32 lanes][8 slots]
-    int4* ring_in;                // blocks of the row above my strip
-    int4* ring_out;               // blocks of my last row, for the next strip
-    bool  has_consumer;
-    int   sigma31, wrap0;
-    // ---- flush role (lane = 8*fk + fe)
-    int fk, fe;
-    int rowmask;                  // bit c: row r0 + c + 8*fk exists
-    long long g0;                 // int4 index of my flush target at t = 0, c = 0
-    long long q4;                 // int4 distance between the targets of rows l and l+1
-    int fcol0;                    // column of element 0 of my flush block at t = 0, c = 0
-    int4* H4; int4* P4;
-    int32_t* H; int32_t* P;
+    // dependency state (registers): block of the row above for this step, its last
+    // element of the previous step (diagonal of my first column), my last cell
+    int A0, A1, A2, A3, dgp, hl;
+    int s0, s1, s2, s3;           // substitution scores of this step's four cells
+    unsigned sa;                  // shared address of my next staging slot
+    unsigned sa_base;             // my row's 1 KB staging region
+    int4* ring_in;                // blocks of the row above my strip (tagged)
+    int4* ring_out;               // blocks of my last row, for the next strip of the band
+    int4* gout;                   // same, for the next band (global): slot of block t - lane
+    bool  has_in;                 // a strip above exists
+    bool  out_ring, out_glob;     // THIS LANE hands blocks on (lane 31 only): to the ring / to global
+    int   jmax;
 
-    template <bool EDGE>
-    __device__ __forceinline__ void step(const int t)
+    __device__ __forceinline__ void scores(const unsigned aword)
     {
-        // ---------------- cells ----------------
         const unsigned x = aword ^ b4;
-        const int s0 = (x & 0x000000ffu) ? sx : sm;       // omp_smithW.c:394-399
-        const int s1 = (x & 0x0000ff00u) ? sx : sm;
-        const int s2 = (x & 0x00ff0000u) ? sx : sm;
-        const int s3 = (x & 0xff000000u) ? sx : sm;
-        const int W[8] = {B[0], B[1], B[2], B[3], A[0], A[1], A[2], A[3]};
-        const int dg = W[3 - MU], u0 = W[4 - MU], u1 = W[5 - MU], u2 = W[6 - MU], u3 = W[7 - MU];
+        s0 = (x & 0x000000ffu) ? sx : sm;       // omp_smithW.c:394-399
+        s1 = (x & 0x0000ff00u) ? sx : sm;
+        s2 = (x & 0x00ff0000u) ? sx : sm;
+        s3 = (x & 0xff000000u) ? sx : sm;
+    }
+
+    // one step.  EDGE: handles the zero column / not-yet-started lanes (first 4 groups) and
+    // the end of the producer's row (last groups).  next_word: packed characters of the
+    // NEXT step (its scores are computed in the shadow of the shuffles).
+    template <bool EDGE>
+    __device__ __forceinline__ void step(const int t, const unsigned next_word,
+                                         const int4* in_next, const int want_next, const int out_slot,
+                                         const int out_tag)
+    {
+        const int j = t - lane;
+        const bool poll = has_in && (!EDGE || t + 1 <= jmax);
+        // block t+1 of the strip above (lane 0's row above for the next step): first try early
+        int4 v = make_int4(0, 0, 0, 0);
+        if (poll) v = lds_volatile_int4(in_next);
+
         // K = max(left+gap|LEFT, up+gap|UP, diag+s|DIAG, 0|NONE)     (omp_smithW.c:339-381)
-        int k0 = __viaddmax_s32(hl, gl, __viaddmax_s32(u0, gu, __viaddmax_s32(dg, s0, kTieNone)));
-        if (EDGE) { const int c = 4 * t + cbase;     if ((unsigned)(c - 1) >= (unsigned)m) k0 = kTieNone; }
+        const int p0 = __viaddmax_s32(dgp, s0, kTieNone);
+        const int p1 = __viaddmax_s32(A0, s1, kTieNone);
+        const int p2 = __viaddmax_s32(A1, s2, kTieNone);
+        const int p3 = __viaddmax_s32(A2, s3, kTieNone);
+        const int t0 = __viaddmax_s32(A0, gu, p0);
+        const int t1 = __viaddmax_s32(A1, gu, p1);
+        const int t2 = __viaddmax_s32(A2, gu, p2);
+        const int t3 = __viaddmax_s32(A3, gu, p3);
+        dgp = A3;
+        int k0 = __viaddmax_s32(hl, gl, t0);
+        if (EDGE) { if (j <= 0) k0 = kTieNone; }
         const int h0 = k0 & ~15;
-        int k1 = __viaddmax_s32(h0, gl, __viaddmax_s32(u1, gu, __viaddmax_s32(u0, s1, kTieNone)));
-        if (EDGE) { const int c = 4 * t + cbase + 1; if ((unsigned)(c - 1) >= (unsigned)m) k1 = kTieNone; }
+        const int n0 = __shfl_up_sync(0xffffffffu, h0, 1);
+        int k1 = __viaddmax_s32(h0, gl, t1);
+        if (EDGE) { if (j < 0) k1 = kTieNone; }
         const int h1 = k1 & ~15;
-        int k2 = __viaddmax_s32(h1, gl, __viaddmax_s32(u2, gu, __viaddmax_s32(u1, s2, kTieNone)));
-        if (EDGE) { const int c = 4 * t + cbase + 2; if ((unsigned)(c - 1) >= (unsigned)m) k2 = kTieNone; }
+        const int n1 = __shfl_up_sync(0xffffffffu, h1, 1);
+        int k2 = __viaddmax_s32(h1, gl, t2);
+        if (EDGE) { if (j < 0) k2 = kTieNone; }
         const int h2 = k2 & ~15;
-        int k3 = __viaddmax_s32(h2, gl, __viaddmax_s32(u3, gu, __viaddmax_s32(u2, s3, kTieNone)));
-        if (EDGE) { const int c = 4 * t + cbase + 3; if ((unsigned)(c - 1) >= (unsigned)m) k3 = kTieNone; }
+        const int n2 = __shfl_up_sync(0xffffffffu, h2, 1);
+        int k3 = __viaddmax_s32(h2, gl, t3);
+        if (EDGE) { if (j < 0) k3 = kTieNone; }
         const int h3 = k3 & ~15;
+        const int n3 = __shfl_up_sync(0xffffffffu, h3, 1);
         hl = h3;
-        rmax = __vimax3_s32(rmax, k0, k1);
-        rmax = __vimax3_s32(rmax, k2, k3);
 
-        // ---------------- stage my block, hand my row to the next strip ----------------
-        stage[lane * 8 + ((t + lane) & 7)] = make_int4(k0, k1, k2, k3);
-        if (has_consumer && lane == 31) {
-            const int qb31 = t - 31 - sigma31;
-            if (!EDGE || qb31 >= 0) ring_out[qb31 & (kRingBlocks - 1)] = make_int4(h0, h1, h2, h3);
-        }
-        // ---------------- pass my block down one lane ----------------
-        B[0] = A[0]; B[1] = A[1]; B[2] = A[2]; B[3] = A[3];
-        A[0] = __shfl_up_sync(0xffffffffu, h0, 1);
-        A[1] = __shfl_up_sync(0xffffffffu, h1, 1);
-        A[2] = __shfl_up_sync(0xffffffffu, h2, 1);
-        A[3] = __shfl_up_sync(0xffffffffu, h3, 1);
-        if (lane == 0) {
-            const int4 v = ring_in[(t + 1 + wrap0) & (kRingBlocks - 1)];
-            A[0] = v.x; A[1] = v.y; A[2] = v.z; A[3] = v.w;
-        }
-        aword = __ldg(aw + t + 1);
-        __syncwarp();
+        // ---------------- stage my packed block for the writer ----------------
+#ifndef SWB_X_NOSTAGE
+        asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(sa), "r"(k0), "r"(k1), "r"(k2), "r"(k3) : "memory");
+#endif
+        sa = ((sa + 16u) & (unsigned)(kT * 16 - 1)) | sa_base;
 
-        // ---------------- write out the rows that completed 8 blocks ----------------
-        // rows l == t+1 (mod 8): lane 8*fk+fe writes block (step t-7+fe) of row c + 8*fk
+        // ---------------- hand my last row to the next strip (lane 31 only) ----------------
         {
-            const int c  = (t + 1) & 7;
-            const int lk = c + 8 * fk;
-            const int4 kv = stage[lk * 8 + ((2 * (t + 1) + fe) & 7)];
-            const int4 hv = make_int4(kv.x >> 4, kv.y >> 4, kv.z >> 4, kv.w >> 4);
-            const int4 pv = make_int4(kv.x & 3, kv.y & 3, kv.z & 3, kv.w & 3);
-            const long long g = g0 + t + c * q4;
-            if (!EDGE) {
-                if ((rowmask >> c) & 1) { st_cs_int4(H4 + g, hv); st_cs_int4(P4 + g, pv); }
-            } else {
-                if ((rowmask >> c) & 1) {
-                    const int col = fcol0 + 4 * t - c * (4 + MU);
-                    const int hh[4] = {hv.x, hv.y, hv.z, hv.w};
-                    const int pp[4] = {pv.x, pv.y, pv.z, pv.w};
+            const bool started = !EDGE || j >= 0;
+            sts_volatile_int4_if(ring_out + out_slot, make_int4(h0 | out_tag, h1, h2, h3 | out_tag), out_ring && started);
+            st_cg_int4_if(gout, make_int4(h0 | 1, h1, h2, h3 | 1), out_glob && started);
+            gout += 1;                                            // block j+1 next step
+        }
+        // ---------------- scores of the next step ----------------
+        scores(next_word);
+
+        // ---------------- the row above, for the next step ----------------
+        if (poll) {
+            int spins = 0;
+            while (((v.x & 3) != want_next) | ((v.w & 3) != want_next)) {
+                if (++spins > 32) __nanosleep(32);
+                v = lds_volatile_int4(in_next);
+            }
+        }
+        const bool l0 = (lane == 0);
+        A0 = l0 ? (v.x & ~15) : n0;
+        A1 = l0 ? v.y : n1;
+        A2 = l0 ? v.z : n2;
+        A3 = l0 ? (v.w & ~15) : n3;
+    }
+};
+
+__device__ __forceinline__ void compute_strip(const FillParams& p, Strip& S, const unsigned* aw,
+                                              volatile int* staged, volatile int* drained,
+                                              volatile int* consumed_in, volatile int* consumed_out,
+                                              const bool ring_consumer, const long long strip)
+{
+    const int lane = S.lane;
+    trace_stamp(p, strip, 0, lane);
+    unsigned cur[kGroup + 1], nxt[kGroup];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if ((unsigned)(col + e) <= (unsigned)m) { H[4 * g + e] = hh[e]; P[4 * g + e] = pp[e]; }
+    for (int i = 0; i < kGroup; ++i) cur[i] = __ldg(aw + i);
+
+    // first input block (block 0 -> ring index 32, epoch 0 -> tag 1); all lanes poll
+    if (S.has_in) {
+        int4 v = lds_volatile_int4(S.ring_in + 32);
+        while (((v.x & 3) != 1) | ((v.w & 3) != 1)) { __nanosleep(SWB_X_GATESLEEP); v = lds_volatile_int4(S.ring_in + 32); }
+        if (lane == 0) { S.A0 = v.x & ~15; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w & ~15; }
+    }
+    trace_stamp(p, strip, 1, lane);
+    S.scores(cur[0]);
+
+    const int gtail = (p.jmax - 8) >> 3;          // groups g <= gtail: t+1 <= jmax for all their steps
+    for (int g = 0; g < p.ngroups; ++g) {
+        if (g == 4) trace_stamp(p, strip, 2, lane);
+        if (g == 8) trace_stamp(p, strip, 3, lane);
+        const int t0 = g * kGroup;
+        // ---- staging ring space: the writer must have drained the slots this group overwrites
+        if (g > kStageSlack) {
+            while (*drained < g - kStageSlack) { }
+        }
+        // ---- hand-off ring space (blocks up to t0+7-31 are written in this group)
+        if (ring_consumer && t0 - 80 > 0) { while (*consumed_out < t0 - 80) { } }
+        if (S.has_in && lane == 0) *consumed_in = t0;
+        // ---- sequence words of the next group
+#pragma unroll
+        for (int i = 0; i < kGroup; ++i) nxt[i] = __ldg(aw + t0 + kGroup + i);
+        cur[kGroup] = nxt[0];
+
+        // consumer side: block t -> ring index (t+32)&63, epoch ((t+32)>>6)&1
+        const int4* in_base  = S.ring_in + ((t0 + 32) & (kRing - 1));
+        const int4* in_wrap  = S.ring_in + ((t0 + 40) & (kRing - 1));
+        const int   want     = 1 + (((t0 + 32) >> 6) & 1);
+        const int   want_w   = 1 + (((t0 + 40) >> 6) & 1);
+        // producer side: block t-31 -> ring index (t+1)&63, epoch ((t+1)>>6)&1
+        const int   ob       = (t0 & (kRing - 1)) + 1;
+        const int   ob_w     = (t0 + 8) & (kRing - 1);
+        const int   otag     = 1 + ((t0 >> 6) & 1);
+        const int   otag_w   = 1 + (((t0 + 8) >> 6) & 1);
+
+        if (g >= 4 && g <= gtail) {
+#pragma unroll
+            for (int i = 0; i < kGroup; ++i) {
+                const bool last = (i == kGroup - 1);
+                S.template step<false>(t0 + i, cur[i + 1], last ? in_wrap : in_base + i + 1, last ? want_w : want,
+                                       last ? ob_w : ob + i, last ? otag_w : otag);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kGroup; ++i) {
+                const bool last = (i == kGroup - 1);
+                S.template step<true>(t0 + i, cur[i + 1], last ? in_wrap : in_base + i + 1, last ? want_w : want,
+                                      last ? ob_w : ob + i, last ? otag_w : otag);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kGroup; ++i) cur[i] = nxt[i];
+        // ---- publish the staged group to the writer
+        __syncwarp();
+#ifndef SWB_X_NOFENCE
+        __threadfence_block();
+#endif
+        if (lane == 0) *staged = g + 1;
+    }
+    trace_stamp(p, strip, 4, lane);
+}
+
+// ---------------------------------------------------------------------------------
+// writer warp: drains the staging ring of one strip into H and P
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void writer_strip(const FillParams& p, const long long r0, const int lane,
+                                             const int* stage /* [32][kRowInts] */, int4* rowtab, int* ftab,
+                                             volatile int* staged, volatile int* drained, const long long strip)
+{
+    // per-row constants: round r flushes, for row l, the 32 columns 32r-E .. 32r-E+31 whose
+    // first element sits on a 128-byte line of H (and P); E is the smallest such offset for
+    // which lane l has finished those columns by the end of compute group r
+    const long long row = r0 + lane;
+    const int ph = (int)((row * p.pitch) & 31);
+    const int d  = (lane + ((31 - ph) >> 2)) >> 3;
+    const int E  = 32 * d + ph;
+    const long long G0 = row * p.pitch - E;                      // multiple of 32
+    const int F  = (8 * lane - E) & (kRowInts - 1);              // ring index of column c is (c + 8l) mod kRowInts
+    const unsigned long long hb = (unsigned long long)(p.H + G0);
+    const unsigned long long pb = (unsigned long long)(p.P + G0);
+    rowtab[lane] = make_int4((int)(unsigned)hb, (int)(unsigned)(hb >> 32), (int)(unsigned)pb, (int)(unsigned)(pb >> 32));
+    ftab[lane] = F;
+    ftab[32 + lane] = E;
+    const unsigned rowmask = __ballot_sync(0xffffffffu, row <= p.n);
+    const int Emax = __reduce_max_sync(0xffffffffu, E);
+    const int Emin = __reduce_min_sync(0xffffffffu, E);
+    __syncwarp();
+
+#ifndef SWB_X_FINETRACE
+    trace_stamp(p, strip, 5, lane);
+#endif
+#ifdef SWB_X_NOWRITER
+    return;
+#endif
+    int mx = 0;
+    const int rounds = p.ngroups + kDrainRounds;
+    const int m = (int)p.m;
+    for (int r = 0; r < rounds; ++r) {
+        const int need = min(r + 1, p.ngroups);
+        if (*staged < need) {
+            int spins = 0;
+#ifndef SWB_X_WRITERSLEEP
+#define SWB_X_WRITERSLEEP 64
+#endif
+            while (*staged < need) { if (++spins > 8) __nanosleep(SWB_X_WRITERSLEEP); }
+        }
+#ifndef SWB_X_NOFENCE
+        __threadfence_block();
+#endif
+        const int v = 32 * r + lane;
+        const bool interior = (rowmask == 0xffffffffu) && (32 * r - Emax >= 0) && (32 * r + 31 - Emin <= m);
+        if (interior) {
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) {
+                const int4 tb = rowtab[l];
+                const int idx = (v + ftab[l]) & (kRowInts - 1);
+                const int k = stage[l * kRowInts + idx];
+                int32_t* hp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.y << 32) | (unsigned)tb.x) + v;
+                int32_t* pp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.w << 32) | (unsigned)tb.z) + v;
+                st_cs_int(hp, k >> 4);
+                st_cs_int(pp, k & 3);
+                mx = max(mx, k);
+            }
+        } else {
+#pragma unroll 2
+            for (int l = 0; l < 32; ++l) {
+                const int4 tb = rowtab[l];
+                const int idx = (v + ftab[l]) & (kRowInts - 1);
+                const int c = v - ftab[32 + l];
+                if (((rowmask >> l) & 1u) && c >= 0 && c <= m) {
+                    const int k = stage[l * kRowInts + idx];
+                    int32_t* hp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.y << 32) | (unsigned)tb.x) + v;
+                    int32_t* pp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.w << 32) | (unsigned)tb.z) + v;
+                    st_cs_int(hp, k >> 4);
+                    st_cs_int(pp, k & 3);
+                    mx = max(mx, k);
                 }
             }
         }
         __syncwarp();
+        if (lane == 0) *drained = r + 1;
     }
-};
+    // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel)
+#ifndef SWB_X_FINETRACE
+    trace_stamp(p, strip, 6, lane);
+#endif
+    const int hm = __reduce_max_sync(0xffffffffu, mx) >> 4;
+    if (lane == 0) {
+        p.strip_max[strip] = hm;
+        if (hm > 0) atomicMax(p.gmax, hm);
+    }
+}
 
-template <int MU>
-__global__ void __launch_bounds__(32 * kMaxWarps)
+// ---------------------------------------------------------------------------------
+// loader warp: copies the tagged last row of the band above from global memory (L2)
+// into the first hand-off ring of this band
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void loader_band(const int4* src, const int nblocks, int4* ring, const int lane,
+                                            volatile int* consumed)
+{
+    int base = 0;
+    int idle = 0;
+    while (base < nblocks) {
+        const int limit = min(nblocks, *consumed + kRing);
+        const int j = base + lane;
+        bool ok = false;
+        if (j < limit) {
+            const int4 v = ld_cg_int4(src + j);
+            ok = ((v.x & 3) == 1) && ((v.w & 3) == 1);
+            if (ok) {
+                const int tag = 1 + (((j + 32) >> 6) & 1);
+                sts_volatile_int4(ring + ((j + 32) & (kRing - 1)),
+                                  make_int4((v.x & ~15) | tag, v.y, v.z, (v.w & ~15) | tag));
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        const int lead = (mask == 0xffffffffu) ? 32 : (__ffs(~mask) - 1);
+        base += lead;
+        if (lead == 0) { if (++idle > 2) __nanosleep(idle > 64 ? 400 : 60); } else idle = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// The fill kernel.  grid = number of bands, block = 32*(2*wpc+1) threads:
+// warps [0,wpc) compute, [wpc,2wpc) write, warp 2wpc loads the band boundary.
+// dynamic smem = wpc * (32*kRowInts*4 + kRing*16 + 32*16 + 64*4) bytes.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * (2 * kMaxWpc + 1))
 fill_kernel(const FillParams p)
 {
-    extern __shared__ int4 smem4[];
+    extern __shared__ __align__(1024) int4 smem4[];
     __shared__ int s_band;
-    __shared__ int s_avail[kMaxWarps + 1];      // [w]: blocks of strip w-1's last row present in ring w
-    __shared__ int s_consumed[kMaxWarps + 1];   // [w]: ring w entries below this index are free
+    __shared__ int s_staged[kMaxWpc], s_drained[kMaxWpc], s_consumed[kMaxWpc + 1];
 
     const int lane = threadIdx.x & 31;
     const int w    = threadIdx.x >> 5;
-    const int wpc  = blockDim.x >> 5;
+    const int wpc  = p.wpc;
+
+    int4* stage4  = smem4;                                       // [wpc][32][kT]
+    int4* rings   = stage4 + (size_t)wpc * 32 * kT;              // [wpc][kRing]
+    int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc][32]
+    int*  ftabs   = reinterpret_cast<int*>(rowtabs + (size_t)wpc * 32);   // [wpc][64]
 
     if (threadIdx.x == 0) s_band = atomicAdd(p.ticket, 1);
-    if (threadIdx.x <= kMaxWarps) { s_avail[threadIdx.x] = 0; s_consumed[threadIdx.x] = 0; }
+    if (threadIdx.x < kMaxWpc) { s_staged[threadIdx.x] = 0; s_drained[threadIdx.x] = 0; }
+    if (threadIdx.x <= kMaxWpc) s_consumed[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < wpc * kRing; i += blockDim.x) rings[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
     const int band = s_band;
     const long long band_r0 = 1 + (long long)band * wpc * 32;
-    const int* prog_in = p.progress + band;          // written by band-1 ([0] is pre-armed)
-    int* prog_out      = p.progress + band + 1;
 
-    // CTA start gate: nobody spins on shared memory until the band above has produced
-    // the first blocks of its last row.
-    if (w == 0) {
-        const int phi_prod = (int)(((band_r0 - 1) * p.pitch) & 3);
-        const int qbp = (int)((p.m + phi_prod) >> 2) + 1;
-        const int want = min(32, qbp);
-        while (ld_acquire_gpu(prog_in) < want) __nanosleep(256);
+    if (w < wpc) {
+        // ------------------------------------------------ compute
+        const long long r0 = band_r0 + 32LL * w;
+        if (r0 > p.n) return;
+        Strip S;
+        S.lane = lane;
+        const long long row = r0 + lane;
+        S.b4 = (row <= p.n) ? (unsigned)p.b[row - 1] * 0x01010101u : 0u;
+        // keep the scoring constants in registers: a shuffle result is opaque to ptxas, which
+        // otherwise re-reads them from the constant bank at the head of every step, on the
+        // dependency chain
+        S.sm = __shfl_sync(0xffffffffu, p.s_match, 0);
+        S.sx = __shfl_sync(0xffffffffu, p.s_mismatch, 0);
+        S.gu = __shfl_sync(0xffffffffu, p.g_up, 0);
+        S.gl = __shfl_sync(0xffffffffu, p.g_left, 0);
+        S.A0 = S.A1 = S.A2 = S.A3 = 0; S.dgp = 0; S.hl = 0;
+        S.sa_base = (unsigned)__cvta_generic_to_shared(stage4 + ((size_t)w * 32 + lane) * kT);
+        S.sa = S.sa_base + 16u * (unsigned)lane;                 // slot (t + lane) & (kT-1) at t = 0
+        S.ring_in  = rings + (size_t)w * kRing;
+        S.ring_out = rings + (size_t)(w + 1 < wpc ? w + 1 : w) * kRing;
+        S.jmax = p.jmax;
+        S.has_in = (r0 > 1);
+        const bool next_row = (r0 + 32 <= p.n);                  // a strip below exists
+        const bool ring_consumer = next_row && (w + 1 < wpc);
+        S.out_ring = ring_consumer && lane == 31;
+        S.out_glob = next_row && (w + 1 == wpc) && lane == 31;
+        // block j = t - lane of step t goes to gout[j]; the pointer advances one block per step
+        // (only lane 31's copy is ever dereferenced, from t = 31 on)
+        S.gout = p.boundary + (size_t)(next_row && (w + 1 == wpc) ? band : 0) * p.bstride - lane;
+        const unsigned* aw = p.a4 + kAPad - lane;                // aw[t] = characters of block t - lane
+        compute_strip(p, S, aw, s_staged + w, s_drained + w, s_consumed + w, s_consumed + w + 1, ring_consumer,
+                      (r0 - 1) >> 5);
+    } else if (w < 2 * wpc) {
+        // ------------------------------------------------ writer
+        const int cw = w - wpc;
+        const long long r0 = band_r0 + 32LL * cw;
+        if (r0 > p.n) return;
+        writer_strip(p, r0, lane, reinterpret_cast<const int*>(stage4 + (size_t)cw * 32 * kT),
+                     rowtabs + (size_t)cw * 32, ftabs + (size_t)cw * 64, s_staged + cw, s_drained + cw,
+                     (r0 - 1) >> 5);
+    } else {
+        // ------------------------------------------------ loader
+        if (band == 0 || band_r0 > p.n) return;
+        loader_band(p.boundary + (size_t)(band - 1) * p.bstride, p.jmax + 1, rings, lane, s_consumed);
     }
-    __syncthreads();
-
-    const long long r0 = band_r0 + 32LL * w;
-    if (r0 > p.n) return;
-
-    Strip<MU> S;
-    S.lane = lane;
-    const int phi0 = (int)((r0 * p.pitch) & 3);
-    const int lm   = phi0 + lane * MU;
-    const int sigma = lm >> 2;
-    const int phil  = lm & 3;
-    S.sigma31 = (phi0 + 31 * MU) >> 2;
-    S.wrap0   = (phi0 < MU) ? 1 : 0;
-    S.cbase   = -lane * (4 + MU) - phi0;
-    S.m       = (int)p.m;
-    const long long row = r0 + lane;
-    const bool row_ok = row <= p.n;
-    S.b4 = row_ok ? (unsigned)p.b[row - 1] * 0x01010101u : 0u;
-    S.aw = p.a4 + (size_t)(3 - phil) * p.a4_stride + kAOff - lane - sigma;
-    S.sm = p.s_match; S.sx = p.s_mismatch; S.gu = p.g_up; S.gl = p.g_left;
-    S.stage    = smem4 + w * kWarpSmemBlocks;
-    S.ring_in  = S.stage + 32 * kGroup;
-    S.ring_out = S.ring_in + kWarpSmemBlocks;
-    S.has_consumer = (w + 1 < wpc) && (r0 + 32 <= p.n);
-    const bool band_last  = (w + 1 == wpc) && (r0 + 32 <= p.n);
-    const bool src_global = (w == 0);
-    S.fk = lane >> 3; S.fe = lane & 7;
-    S.rowmask = 0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) S.rowmask |= (r0 + c + 8 * S.fk <= p.n) ? (1 << c) : 0;
-    const long long Z = r0 * p.pitch - phi0;                 // multiple of 4
-    S.q4 = (p.pitch - 4 - MU) >> 2;
-    S.g0 = (Z >> 2) - 7 + S.fe + (long long)(8 * S.fk) * S.q4;
-    S.fcol0 = 4 * (S.fe - 7) - (8 * S.fk) * (4 + MU) - phi0;
-    S.H4 = reinterpret_cast<int4*>(p.H); S.P4 = reinterpret_cast<int4*>(p.P);
-    S.H = p.H; S.P = p.P;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { S.A[e] = 0; S.B[e] = 0; }
-    S.hl = 0; S.rmax = 0;
-    S.aword = __ldg(S.aw);
-
-    // fast (unmasked) steps: every lane's block inside columns [1, m] for steps t-7..t
-    const int t_lo = (1 + 31 * (4 + MU) + phi0 + 3) >> 2;
-    const int t_hi = (int)((p.m - 3 + phi0) >> 2);            // floor; may be negative
-
-    // producer row (row r0-1) as seen by lane 0 when it comes from global memory
-    const int phi_prod = (phi0 - MU) & 3;
-    const int qbp = (int)((p.m + phi_prod) >> 2) + 1;
-    const int4* Hprev4 = reinterpret_cast<const int4*>(p.H) + (((r0 - 1) * p.pitch) >> 2);
-    int gl_loaded = 0;
-    int cached_avail = 0;
-    volatile int* v_avail = s_avail;
-    volatile int* v_consumed = s_consumed;
-
-    for (int tg = 0; tg < p.steps; tg += kGroup) {
-        // ---- the blocks of the row above that this group will read: index <= tg+8+wrap0
-        if (src_global) {
-            const int need = min(tg + 9 + S.wrap0, qbp);
-            while (gl_loaded < need) {
-                const int want = min(gl_loaded + 32, qbp);
-                while (ld_acquire_gpu(prog_in) < want) __nanosleep(64);
-                const int blk = gl_loaded + lane;
-                int4 v = make_int4(0, 0, 0, 0);
-                if (blk < qbp) v = ld_cg_int4(Hprev4 + blk);
-                S.ring_in[blk & (kRingBlocks - 1)] = make_int4(v.x << 4, v.y << 4, v.z << 4, v.w << 4);
-                gl_loaded += 32;
-                __syncwarp();
-            }
-        } else {
-            const int need = min(tg + 9 + S.wrap0, p.qbmax);
-            if (cached_avail < need) {
-                do { cached_avail = v_avail[w]; } while (cached_avail < need);
-                __threadfence_block();
-            }
-            if (lane == 0) v_consumed[w] = tg + 1 + S.wrap0;
-        }
-        if (tg == 0 && lane == 0) {
-            const int4 va = S.ring_in[S.wrap0];
-            S.A[0] = va.x; S.A[1] = va.y; S.A[2] = va.z; S.A[3] = va.w;
-            if (S.wrap0) { const int4 vb = S.ring_in[0]; S.B[0] = vb.x; S.B[1] = vb.y; S.B[2] = vb.z; S.B[3] = vb.w; }
-        }
-        // ---- room in the next strip's ring for the 8 blocks lane 31 is about to write
-        if (S.has_consumer) {
-            const int last = tg + 7 - 31 - S.sigma31;
-            if (last >= kRingBlocks)
-                while (last - kRingBlocks >= v_consumed[w + 1]) { }
-        }
-        // ---- 8 steps
-        if (tg - 7 >= t_lo && tg + 7 <= t_hi) {
-#pragma unroll
-            for (int j = 0; j < kGroup; ++j) S.template step<false>(tg + j);
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < kGroup; ++j) S.template step<true>(tg + j);
-        }
-        // ---- publish
-        const int done = tg + 8 - 31 - S.sigma31;       // blocks of my last row finished so far
-        if (S.has_consumer && done > 0 && lane == 31) {
-            __threadfence_block();
-            v_avail[w + 1] = done;
-        }
-        if (band_last && lane == 0) {
-            // row 31 was written out at the step t == 6 (mod 8) of this group: blocks <= tg+6-31-sigma31
-            const int vis = tg + 7 - 31 - S.sigma31;
-            if (vis > 0) st_release_gpu(prog_out, vis);   // cumulative over the __syncwarp'd stores of the other lanes
-        }
-    }
-
-    // ---- per-row maxima (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel)
-    int hmax = row_ok ? (S.rmax >> 4) : 0;
-    if (row_ok) p.row_max[row] = hmax;
-    const int wm = __reduce_max_sync(0xffffffffu, hmax);
-    if (lane == 0 && wm > 0) atomicMax(p.gmax, wm);
 }
 
 // ---------------------------------------------------------------------------------
 // maxPos with the reference's tie-break: among the cells with H == global max, the one
 // with the smallest i+j, then the largest i (omp_smithW.c:203-215,282-291,384-387).
-// Only rows whose row maximum equals the global maximum are scanned.
+// Only rows of strips whose maximum equals the global maximum are scanned.
 // ---------------------------------------------------------------------------------
 __global__ void argmax_kernel(const int32_t* __restrict__ H, long long pitch, long long m, long long n,
-                              const int* __restrict__ row_max, const int* __restrict__ gmax,
+                              const int* __restrict__ strip_max, const int* __restrict__ gmax,
                               unsigned long long* key)
 {
     const int g = *gmax;
@@ -385,7 +547,7 @@ __global__ void argmax_kernel(const int32_t* __restrict__ H, long long pitch, lo
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long r = 1 + warp; r <= n; r += nwarps) {
-        if (row_max[r] != g) continue;
+        if (strip_max[(r - 1) >> 5] != g) continue;
         const int32_t* Hr = H + r * pitch;
         for (long long j0 = 1; j0 <= m; j0 += 32) {
             const long long j = j0 + lane;

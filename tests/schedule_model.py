@@ -1,152 +1,276 @@
-"""Lane-vectorised numpy model of fill_kernel's schedule (swb_kernels.cuh).
+"""Lane-vectorised numpy model of fill_kernel's schedule (smith-waterman_b200/csrc/swb_kernels.cuh).
 
-It transliterates the kernel's index arithmetic -- per-row 16-byte block phase,
-lane skew sigma, the 8-register window of the row above, the staging ring and the
-write-out addressing, the strip -> strip hand-off indices -- with the 32 lanes of a
-warp as a numpy axis.  Strips run one after the other (no concurrency), so it checks
-the MATH of the schedule, not the synchronisation.  tests/test_schedule_model.py
-compares it with the oracle; the GPU tests compare the real kernel.
+It transliterates the kernel's index arithmetic -- blocks of four columns per lane and
+step, the staging ring and the writer's per-row 128-byte segmentation (E, F), the tagged
+strip -> strip hand-off ring (slot / epoch arithmetic, back-pressure rule), the tagged
+band boundary rows and the loader -- with the 32 lanes of a warp as a numpy axis.
+
+Compute warps, writer warps and loader warps are ACTORS that advance one group / round
+at a time under a scheduling policy ("eager": consumers and writers first, "lazy":
+producers run as far ahead as the back-pressure rules allow, writers as late as
+possible, "random").  Poisoned rings make any read of a slot that was overwritten too
+early, or not yet written, show up as a wrong result; a state in which no actor can run
+is reported as a deadlock.  It checks the MATH and the flow-control RULES of the schedule,
+not the memory model; the GPU tests check the real kernel.
 """
 import numpy as np
 
 TIE_NONE, TIE_DIAG, TIE_UP, TIE_LEFT = 8, 7, 5, 2
+KT = 64
+ROW_INTS = 4 * KT
 RING = 64
-AOFF = 64
+GROUP = 8
+DRAIN_ROUNDS = 2
+STAGE_SLACK = KT // GROUP - 2
+POISON = -(1 << 40)
 
 
-def build_a4(a: np.ndarray, stride: int) -> np.ndarray:
-    m = len(a)
-    out = np.zeros((4, stride, 4), dtype=np.int64)
-    for s in range(4):
-        k = np.arange(stride)
-        for e in range(4):
-            idx = 4 * (k - AOFF) + s - 4 + e
-            ok = (idx >= 0) & (idx < m)
-            out[s, ok, e] = a[idx[ok]]
-    return out            # bytes of each word, little-endian order e = 0..3
+class Deadlock(AssertionError):
+    pass
 
 
-def fill_model(a, b, scoring=(3, -3, -2), wpc=4, pitch=None, check_fast=True):
+def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed=0):
     a = np.asarray(a, dtype=np.int64)
     b = np.asarray(b, dtype=np.int64)
     m, n = len(a), len(b)
     pitch = pitch or m + 1
-    MU = pitch & 3
     match, mismatch, gap = scoring
     sm, sx = 16 * match + TIE_DIAG, 16 * mismatch + TIE_DIAG
     gu, gl = 16 * gap + TIE_UP, 16 * gap + TIE_LEFT
-    qbmax = ((m + 3) >> 2) + 1
-    steps = (qbmax + 62 + 7) // 8 * 8
-    stride = AOFF + steps + 8
-    a4 = build_a4(a, stride)
-    total = (n + 1) * pitch + 8
+    jmax = m >> 2
+    ngroups = (jmax + 1 + 31 + GROUP - 1) // GROUP
+    gtail = (jmax - 8) >> 3
+    bstride = ngroups * GROUP
+    strips = (n + 31) // 32
+    nbands = (strips + wpc - 1) // wpc
+    lane = np.arange(32)
+    rng = np.random.default_rng(seed)
+
+    # packed a: chars of block j (columns 4j..4j+3, column c reads a[c-1])
+    def achars(j):                      # j: (32,) -> (32, 4)
+        c = 4 * j[:, None] + np.arange(4)[None, :]
+        idx = c - 1
+        ok = (idx >= 0) & (idx < m)
+        out = np.zeros((32, 4), dtype=np.int64)
+        out[ok] = a[idx[ok]]
+        return out
+
+    total = (n + 1) * pitch
     H = np.full(total, -777, dtype=np.int64)
     P = np.full(total, -777, dtype=np.int64)
     H[: m + 1] = 0
     P[: m + 1] = 0
-    row_max = np.zeros(n + 1, dtype=np.int64)
-    lane = np.arange(32)
-    strips = (n + 31) // 32
-    ring_next = None          # blocks written by the previous strip's lane 31 (dict qb -> 4 ints)
-    for s_idx in range(strips):
-        w = s_idx % wpc
-        r0 = 1 + 32 * s_idx
-        phi0 = (r0 * pitch) & 3
-        lm = phi0 + lane * MU
-        sigma, phil = lm >> 2, lm & 3
-        sigma31 = (phi0 + 31 * MU) >> 2
-        wrap0 = 1 if phi0 < MU else 0
-        cbase = -lane * (4 + MU) - phi0
-        row = r0 + lane
-        row_ok = row <= n
-        bch = np.where(row_ok, b[np.minimum(row, n) - 1], 0)
-        acopy = 3 - phil
-        aoff = AOFF - lane - sigma
-        has_consumer = (w + 1 < wpc) and (r0 + 32 <= n)
-        src_global = w == 0
-        # ---- input ring contents
-        phi_prod = (phi0 - MU) & 3
-        qbp = ((m + phi_prod) >> 2) + 1
-        if src_global:
-            base_blk = ((r0 - 1) * pitch) >> 2
+    strip_max = np.zeros(strips, dtype=np.int64)
+    boundary = np.zeros((max(nbands - 1, 0), bstride, 4), dtype=np.int64)     # memset 0 = invalid tags
 
-            def ring_in(idx):
-                if idx < qbp:
-                    return H[4 * (base_blk + idx): 4 * (base_blk + idx) + 4] << 4
-                return np.zeros(4, dtype=np.int64)
+    class Compute:
+        def __init__(self, s):
+            self.s = s
+            self.band, self.w = divmod(s, wpc)
+            self.r0 = 1 + 32 * s
+            rows = self.r0 + lane
+            self.bch = np.where(rows <= n, b[np.minimum(rows, n) - 1], 0)
+            self.A = np.zeros((32, 4), dtype=np.int64)
+            self.dgp = np.zeros(32, dtype=np.int64)
+            self.hl = np.zeros(32, dtype=np.int64)
+            self.g = 0
+            self.started = False
+            self.stage = np.full((32, ROW_INTS), POISON, dtype=np.int64)
+            self.ring = np.zeros((RING, 4), dtype=np.int64)                  # my INPUT ring
+            self.staged = 0
+            self.drained = 0
+            self.consumed = 0                                                  # blocks of my input ring I am done with
+            self.has_in = self.r0 > 1
+            nxt = self.r0 + 32 <= n
+            self.out = 0 if not nxt else (1 if self.w + 1 < wpc else 2)
+
+        def ring_valid(self, j):
+            e = self.ring[(j + 32) & (RING - 1)]
+            want = 1 + (((j + 32) >> 6) & 1)
+            return (e[0] & 3) == want and (e[3] & 3) == want
+
+        def runnable(self):
+            g = self.g
+            if g >= ngroups:
+                return False
+            if g > STAGE_SLACK and self.drained < g - STAGE_SLACK:
+                return False
+            t0 = g * GROUP
+            if self.out == 1 and t0 - 80 > 0 and comp[self.s + 1].consumed < t0 - 80:
+                return False
+            if self.has_in:
+                need = [0] if g == 0 else []
+                need += [t + 1 for t in range(t0, t0 + GROUP) if t + 1 <= jmax]
+                if not all(self.ring_valid(j) for j in need):
+                    return False
+            return True
+
+        def take_input(self, j):
+            assert self.ring_valid(j)
+            e = self.ring[(j + 32) & (RING - 1)].copy()
+            e[0] &= ~15
+            e[3] &= ~15
+            self.A[0] = e
+
+        def run(self):
+            g = self.g
+            t0 = g * GROUP
+            if self.has_in:
+                if g == 0:
+                    self.take_input(0)
+                self.consumed = t0
+            fast = 4 <= g <= gtail
+            for i in range(GROUP):
+                t = t0 + i
+                j = t - lane
+                ch = achars(j)
+                s = np.where(ch == self.bch[:, None], sm, sx)
+                A, hl = self.A, self.hl.copy()
+                k = np.zeros((32, 4), dtype=np.int64)
+                h = np.zeros((32, 4), dtype=np.int64)
+                dg = self.dgp
+                for e in range(4):
+                    ke = np.maximum(np.maximum(hl + gl, A[:, e] + gu), np.maximum(dg + s[:, e], TIE_NONE))
+                    if not fast:
+                        ke = np.where((j < 0) | ((j == 0) & (e == 0)), TIE_NONE, ke)
+                    else:
+                        assert (j >= 1).all()
+                    k[:, e] = ke
+                    h[:, e] = ke & ~15
+                    hl = h[:, e]
+                    dg = A[:, e]
+                self.hl = hl
+                self.dgp = A[:, 3].copy()
+                # stage: lane l, slot (t + l) & (KT-1)
+                slot = (t + lane) & (KT - 1)
+                for e in range(4):
+                    self.stage[lane, 4 * slot + e] = k[:, e]
+                # hand-off of lane 31
+                j31 = t - 31
+                if self.out and (fast or j31 >= 0):
+                    blk = h[31].copy()
+                    if self.out == 1:
+                        tag = 1 + (((t + 1) >> 6) & 1)
+                        blk[0] |= tag
+                        blk[3] |= tag
+                        comp[self.s + 1].ring[(t + 1) & (RING - 1)] = blk
+                    else:
+                        blk[0] |= 1
+                        blk[3] |= 1
+                        boundary[self.band, j31] = blk
+                # row above for the next step
+                newA = np.zeros((32, 4), dtype=np.int64)
+                newA[1:] = h[:-1]
+                self.A = newA
+                if self.has_in and (fast or t + 1 <= jmax):
+                    assert t + 1 <= jmax
+                    self.take_input(t + 1)
+            self.g += 1
+            self.staged = self.g
+
+    class Writer:
+        def __init__(self, s):
+            self.s = s
+            self.c = comp[s]
+            r0 = self.c.r0
+            rows = r0 + lane
+            ph = (rows * pitch) & 31
+            d = (lane + ((31 - ph) >> 2)) >> 3
+            self.E = 32 * d + ph
+            self.G0 = rows * pitch - self.E
+            assert (self.G0 % 32 == 0).all()
+            self.F = (8 * lane - self.E) & (ROW_INTS - 1)
+            self.rowok = rows <= n
+            self.r = 0
+            self.mx = 0
+            self.rounds = ngroups + DRAIN_ROUNDS
+
+        def runnable(self):
+            return self.r < self.rounds and self.c.staged >= min(self.r + 1, ngroups)
+
+        def run(self):
+            r = self.r
+            v = 32 * r + lane
+            interior = self.rowok.all() and 32 * r - self.E.max() >= 0 and 32 * r + 31 - self.E.min() <= m
+            for l in range(32):
+                idx = (v + self.F[l]) & (ROW_INTS - 1)
+                c = v - self.E[l]
+                ok = np.full(32, True) if interior else (self.rowok[l] & (c >= 0) & (c <= m))
+                if interior:
+                    assert self.rowok[l] and (c >= 0).all() and (c <= m).all()
+                k = self.c.stage[l, idx]
+                gi = self.G0[l] + v
+                kk = k[ok]
+                assert (kk != POISON).all(), "writer read a slot that was never written"
+                assert (H[gi[ok]] == -777).all(), "cell written twice"
+                H[gi[ok]] = kk >> 4
+                P[gi[ok]] = kk & 3
+                if kk.size:
+                    self.mx = max(self.mx, int(kk.max()))
+            self.r += 1
+            self.c.drained = self.r
+            if self.r == self.rounds:
+                strip_max[self.s] = self.mx >> 4
+
+    class Loader:
+        def __init__(self, band):
+            self.band = band
+            self.c = comp[band * wpc]
+            self.base = 0
+            self.nblocks = jmax + 1
+
+        def avail(self):
+            limit = min(self.nblocks, self.c.consumed + RING)
+            src = boundary[self.band - 1]
+            n_ok = 0
+            for j in range(self.base, min(limit, self.base + 32)):
+                if (src[j, 0] & 3) == 1 and (src[j, 3] & 3) == 1:
+                    n_ok += 1
+                else:
+                    break
+            return n_ok
+
+        def runnable(self):
+            return self.base < self.nblocks and self.avail() > 0
+
+        def run(self):
+            src = boundary[self.band - 1]
+            for j in range(self.base, self.base + self.avail()):
+                tag = 1 + (((j + 32) >> 6) & 1)
+                blk = src[j].copy()
+                blk[0] = (blk[0] & ~15) | tag
+                blk[3] = (blk[3] & ~15) | tag
+                self.c.ring[(j + 32) & (RING - 1)] = blk
+                self.base += 1
+
+    comp = [Compute(s) for s in range(strips)]
+    writers = [Writer(s) for s in range(strips)]
+    loaders = [Loader(bd) for bd in range(1, nbands)]
+
+    def pick():
+        run_c = [c for c in comp if c.runnable()]
+        run_w = [w for w in writers if w.runnable()]
+        run_l = [l for l in loaders if l.runnable()]
+        if policy == "eager":            # drain first, consumers before producers
+            order = run_w + run_l[::-1] + run_c[::-1]
+        elif policy == "lazy":           # producers as far ahead as allowed, writers last
+            order = run_c + run_l + run_w
         else:
-            prev = ring_next
+            order = run_c + run_w + run_l
+            if order:
+                return order[rng.integers(len(order))]
+        return order[0] if order else None
 
-            def ring_in(idx, prev=prev):
-                return prev.get(idx, np.full(4, 123456, dtype=np.int64))   # stale garbage
-        ring_out = {}
-        A = np.zeros((32, 4), dtype=np.int64)
-        B = np.zeros((32, 4), dtype=np.int64)
-        A[0] = ring_in(wrap0)
-        if wrap0:
-            B[0] = ring_in(0)
-        hl = np.zeros(32, dtype=np.int64)
-        rmax = np.zeros(32, dtype=np.int64)
-        stage = np.zeros((32, 8, 4), dtype=np.int64)
-        t_lo = (1 + 31 * (4 + MU) + phi0 + 3) >> 2
-        t_hi = (m - 3 + phi0) >> 2
-        fk, fe = lane >> 3, lane & 7
-        Z = r0 * pitch - phi0
-        assert Z % 4 == 0
-        q4 = (pitch - 4 - MU) >> 2
-        g0 = (Z >> 2) - 7 + fe + (8 * fk) * q4
-        fcol0 = 4 * (fe - 7) - (8 * fk) * (4 + MU) - phi0
-        for t in range(steps):
-            tg = t - (t % 8)
-            fast = (tg - 7 >= t_lo) and (tg + 7 <= t_hi)
-            aw = a4[acopy, aoff + t]                        # (32, 4) bytes
-            mis = aw != bch[:, None]
-            sc = np.where(mis, sx, sm)
-            W = np.concatenate([B, A], axis=1)
-            dg = W[:, 3 - MU]
-            up = W[:, 4 - MU: 8 - MU]
-            K = np.zeros((32, 4), dtype=np.int64)
-            h = np.zeros((32, 4), dtype=np.int64)
-            left = hl.copy()
-            diag = dg
-            for e in range(4):
-                k = np.maximum(left + gl, np.maximum(up[:, e] + gu, np.maximum(diag + sc[:, e], TIE_NONE)))
-                c = 4 * t + cbase + e
-                valid = (c >= 1) & (c <= m)
-                if fast and check_fast:
-                    assert valid.all(), (s_idx, t, e)
-                k = np.where(valid, k, TIE_NONE)
-                K[:, e] = k
-                h[:, e] = k & ~15
-                left = h[:, e]
-                diag = up[:, e]
-            hl = h[:, 3]
-            rmax = np.maximum(rmax, K.max(axis=1))
-            stage[lane, (t + lane) & 7] = K
-            qb31 = t - 31 - sigma31
-            if has_consumer and qb31 >= 0:
-                ring_out[qb31] = h[31].copy()
-            B = A.copy()
-            A = np.roll(h, 1, axis=0)
-            A[0] = ring_in(t + 1 + wrap0)
-            # ---- write-out
-            c = (t + 1) & 7
-            lk = c + 8 * fk
-            kv = stage[lk, (2 * (t + 1) + fe) & 7]
-            g = g0 + t + c * q4
-            col = fcol0 + 4 * t - c * (4 + MU)
-            rowmask = (r0 + lk) <= n
-            for e in range(4):
-                ok = rowmask & (col + e >= 0) & (col + e <= m)
-                if fast and check_fast:
-                    assert (ok == rowmask).all()
-                idx = 4 * g[ok] + e
-                # every element is written exactly once
-                assert (H[idx] == -777).all(), (s_idx, t, e)
-                H[idx] = kv[ok, e] >> 4
-                P[idx] = kv[ok, e] & 3
-        row_max[row[row_ok]] = (rmax >> 4)[row_ok]
-        ring_next = ring_out
-    Hm = H[: (n + 1) * pitch].reshape(n + 1, pitch)[:, : m + 1]
-    Pm = P[: (n + 1) * pitch].reshape(n + 1, pitch)[:, : m + 1]
-    return Hm, Pm, row_max
+    while True:
+        act = pick()
+        if act is None:
+            break
+        act.run()
+    done = all(c.g == ngroups for c in comp) and all(w.r == w.rounds for w in writers)
+    if not done:
+        raise Deadlock(f"stuck: compute {[c.g for c in comp]} of {ngroups}, writers {[w.r for w in writers]}")
+    Hm = H.reshape(n + 1, pitch)[:, : m + 1]
+    Pm = P.reshape(n + 1, pitch)[:, : m + 1]
+    if pitch > m + 1:
+        assert (H.reshape(n + 1, pitch)[:, m + 1:] == -777).all(), "padding written"
+    return Hm, Pm, strip_max

@@ -61,12 +61,20 @@ def test_product_never_touches_the_oracle():
             assert "sw_oracle" not in txt and "libsworacle" not in txt and "swo_" not in txt, p
 
 
-@pytest.mark.parametrize("m,n,wpc", [(8, 9, 4), (130, 33, 1), (131, 64, 4), (132, 65, 2), (133, 100, 4), (303, 70, 3)])
-def test_schedule_model_reproduces_oracle(oracle, m, n, wpc):
+@pytest.mark.parametrize("m,n,wpc,pitch,policy", [
+    (8, 9, 2, None, "lazy"), (130, 33, 1, None, "lazy"), (131, 64, 2, None, "eager"), (132, 65, 2, 140, "lazy"),
+    (133, 100, 4, None, "random"), (303, 70, 3, None, "lazy"), (1, 40, 2, None, "lazy"), (37, 1, 1, None, "eager"),
+    (700, 97, 2, None, "lazy"), (700, 97, 2, None, "eager"), (1100, 130, 2, 1128, "random"), (600, 200, 1, None, "lazy"),
+])
+def test_schedule_model_reproduces_oracle(oracle, m, n, wpc, pitch, policy):
+    """Index arithmetic and flow-control rules of fill_kernel (staging ring + writer
+    segmentation, tagged hand-off rings, band boundary + loader) on the CPU."""
     from schedule_model import fill_model
     rng = np.random.default_rng(m * 1000 + n)
     acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
     a, b = rng.choice(acgt, m), rng.choice(acgt, n)
     H, P, _ = oracle.fill(a, b)
-    Hm, Pm, rmax = fill_model(a, b, wpc=wpc)
-    assert (Hm == H).all() and (Pm == P).all() and (rmax[1:] == H[1:].max(axis=1)).all()
+    Hm, Pm, smax = fill_model(a, b, wpc=wpc, pitch=pitch, policy=policy, seed=m + n)
+    assert (Hm == H).all() and (Pm == P).all()
+    want = [H[1 + 32 * s: 33 + 32 * s].max() for s in range((n + 31) // 32)]
+    assert list(smax) == want
