@@ -72,22 +72,24 @@ struct Workspace {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+size_t fill_smem_bytes(int wpc)
+{
+    return (size_t)wpc * (swb::kStripRows * swb::kRowInts * sizeof(int) + swb::kRing * sizeof(int4) +
+                          swb::kWriters * 32 * sizeof(int4));
+}
+
 int pick_wpc(int64_t n, const swb_tuning* tuning)
 {
-    int wpc = 2;
+    int wpc = 1;
     if (const char* e = std::getenv("SWB_WPC")) wpc = std::atoi(e);
     if (tuning && tuning->warps_per_band > 0) wpc = tuning->warps_per_band;
     wpc = std::max(1, std::min(wpc, swb::kMaxWpc));
-    const int64_t strips = (n + 31) / 32;
+    while (wpc > 1 && fill_smem_bytes(wpc) + 2048 > 227 * 1024) --wpc;     // 227 KB of shared memory per CTA on sm_100
+    const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
     if (strips < wpc) wpc = (int)strips;
     return wpc;
 }
 
-size_t fill_smem_bytes(int wpc)
-{
-    return (size_t)wpc * (32 * swb::kRowInts * sizeof(int) + swb::kRing * sizeof(int4) + 32 * sizeof(int4) +
-                          64 * sizeof(int));
-}
 
 }  // namespace
 
@@ -184,7 +186,7 @@ int swb_fill_async(const char* a, int64_t m, const char* b, int64_t n,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     const int wpc = pick_wpc(n, tuning);
-    const int64_t strips = (n + 31) / 32;
+    const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
     const int nbands = (int)((strips + wpc - 1) / wpc);
     const int jmax = (int)(m >> 2);                                   // last block with a valid column
     const int ngroups = (jmax + 1 + 31 + swb::kGroup - 1) / swb::kGroup;
@@ -224,7 +226,8 @@ int swb_fill_async(const char* a, int64_t m, const char* b, int64_t n,
         // band-boundary rows carry their validity tag in the data: clear the tags
         if (boundary_bytes) SWB_CUDA(cudaMemsetAsync(ws.boundary, 0, boundary_bytes, st));
         const int prep_blocks = (int)std::min<int64_t>((ws.a4_words + 255) / 256, 1184);
-        swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, ws.a4, ws.a4_words, ws.ticket, ws.gmax, ws.key);
+        swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, ws.a4, ws.a4_words, ws.ticket, ws.gmax, ws.key, ws.strip_max,
+                                                      (long long)strips);
         SWB_CUDA(cudaGetLastError());
 
         swb::FillParams p{};
@@ -239,11 +242,10 @@ int swb_fill_async(const char* a, int64_t m, const char* b, int64_t n,
         p.ticket = ws.ticket; p.strip_max = ws.strip_max; p.gmax = ws.gmax;
         p.trace = tuning ? reinterpret_cast<unsigned long long*>(tuning->trace) : nullptr;
         const size_t smem = fill_smem_bytes(wpc);
-        SWB_CUDA(cudaFuncSetAttribute(swb::fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)fill_smem_bytes(swb::kMaxWpc)));
+        SWB_CUDA(cudaFuncSetAttribute(swb::fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         swb_timer* timer = tuning ? tuning->timer : nullptr;
         if (timer) SWB_CUDA(cudaEventRecord(timer->start, st));
-        swb::fill_kernel<<<nbands, 32 * (2 * wpc + 1), smem, st>>>(p);
+        swb::fill_kernel<<<nbands, swb::fill_block_threads(wpc), smem, st>>>(p);
         SWB_CUDA(cudaGetLastError());
         if (timer) SWB_CUDA(cudaEventRecord(timer->stop, st));
 

@@ -4,29 +4,34 @@
 // (omp_smithW.c:203-216, 331-388, 405-420).  DESIGN.md has the derivation and the
 // measurements; the short version of the fill kernel:
 //
-//  * The matrix is cut into STRIPS of 32 rows.  A COMPUTE warp owns a strip and sweeps it
-//    left to right: lane l owns row r0+l and computes, per STEP t, the BLOCK j = t-l of four
-//    columns 4j..4j+3 (column 0 is the zero boundary column and is computed like any other).
-//    H stays in registers on the dependency chain: the block of the row above arrives by
-//    __shfl_up_sync, the cell to the left is the lane's own previous value.
+//  * The matrix is cut into STRIPS of 32*kR rows.  A COMPUTE warp owns a strip and sweeps it
+//    left to right: lane l owns the kR adjacent rows r0+kR*l .. and computes, per STEP t, the
+//    BLOCK j = t-l of four columns 4j..4j+3 of each of them (column 0 is the zero boundary
+//    column and is computed like any other).  H stays in registers on the dependency chain:
+//    the block of the row above the lane's first row arrives by __shfl_up_sync, the rows of
+//    a lane feed each other directly, the cell to the left is the lane's own previous value.
 //  * A cell is computed on packed keys K = 16*H + tie, tie in {NONE 8, DIAG 7, UP 5, LEFT 2}:
 //    one max over the four candidates reproduces the reference's strict-'>' order
 //    DIAGONAL, UP, LEFT (omp_smithW.c:348-378); P = K&3, H = K>>4.  Three DPX VIADDMNMX per
 //    cell, of which one is on the chain.
-//  * Warp specialisation.  The compute warp only stages its packed block (one 16-byte
-//    STS per lane per step) in a shared-memory ring.  A WRITER warp per strip drains the
-//    ring: for every row it reads 32 consecutive columns (conflict-free LDS.32), unpacks H
-//    and P and stores them with two warp-wide stores that each cover ONE FULL 128-byte
-//    line of the caller's row-major matrix (the segmentation is chosen per row so that
-//    this holds for any pitch).  The writer also keeps the strip maximum for maxPos.
-//  * Strip -> strip hand-off (row 32 of a strip feeds row 1 of the next): lane 31 stores
-//    its H block into a 64-entry shared-memory ring of the next compute warp of the CTA
-//    ("band" = wpc strips); the entry carries an epoch tag in its low bits, so the
+//  * Warp specialisation.  The compute warp only stages its packed blocks (one 16-byte
+//    STS per row per step) in a shared-memory ring.  WRITER warps drain the ring: for
+//    every row they read 32 consecutive columns (conflict-free LDS.32), unpack H and P and
+//    store them with two warp-wide stores that each cover ONE FULL 128-byte line of the
+//    caller's row-major matrix (the segmentation is chosen per row so that this holds for
+//    any pitch).  The writers also keep the strip maximum for maxPos.
+//  * Strip -> strip hand-off (last row of a strip feeds the first row of the next): lane
+//    31 stores its H block into a 64-entry shared-memory ring of the next compute warp of
+//    the CTA ("band" = wpc strips); the entry carries an epoch tag in its low bits, so the
 //    consumer polls the DATA and no fence sits on the dependency chain.  Band -> band goes
 //    through a tagged boundary row in global memory (L2) that a LOADER warp of the next
 //    band copies into that band's first ring.  Bands are claimed from an atomic ticket in
 //    start order, so a waiting band's predecessor is always resident: the whole fill is
 //    ONE launch, anti-diagonals are not launches.
+//  * A compute warp never diverges: every poll is executed by all 32 lanes on a broadcast
+//    address and hand-off stores are PTX-predicated.  (A lane-0-only spin loop leaves the
+//    warp split and every following shuffle takes the divergent slow path: measured 8x
+//    slower steps.)
 //  * maxPos: a second tiny kernel scans only the strips that attain the global maximum,
 //    with the reference's tie-break (first in anti-diagonal order, bottom-left to
 //    top-right; omp_smithW.c:203-215,384-387).
@@ -34,14 +39,30 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef SWB_X_GATESLEEP
+#define SWB_X_GATESLEEP 100
+#endif
+#ifndef SWB_X_WRITERSLEEP
+#define SWB_X_WRITERSLEEP 64
+#endif
+
 namespace swb {
 
-constexpr int kT        = 64;          // staging ring depth in steps (16-byte slots per row)
+#ifndef SWB_ROWS_PER_LANE
+#define SWB_ROWS_PER_LANE 2
+#endif
+constexpr int kR        = SWB_ROWS_PER_LANE;   // adjacent rows per lane
+constexpr int kStripRows = 32 * kR;    // rows per strip (compute warp)
+constexpr int kWriters  = kR;          // writer warps per strip, 32 rows each
+#ifndef SWB_KT
+#define SWB_KT 64
+#endif
+constexpr int kT        = SWB_KT;      // staging ring depth in steps (16-byte slots per row)
 constexpr int kRowInts  = 4 * kT;      // ints per row of the staging ring
 constexpr int kRing     = 64;          // hand-off ring capacity in blocks (power of two)
 constexpr int kGroup    = 8;           // steps per synchronisation group
 constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
-constexpr int kMaxWpc   = 4;           // strips per band (CTA) upper bound
+constexpr int kMaxWpc   = 3;           // strips per band (CTA) upper bound (one scheduler must serve the writers)
 constexpr int kDrainRounds = 2;        // writer rounds after the last compute group
 // writer round r reads steps [8r-8, 8r+7]; compute group g overwrites the slots of group
 // g - kT/8, which rounds <= g - kT/8 + 1 read: g may start once that many rounds are done
@@ -66,7 +87,7 @@ struct FillParams {
     int4*           boundary;              // [nbands][bstride] tagged blocks: last row of band k
     long long       bstride;
     int*            ticket;                // band ticket counter
-    int*            strip_max;             // [nstrips] max H of each strip
+    int*            strip_max;             // [nstrips] max H of each strip (atomicMax by its writers)
     int*            gmax;                  // global max H
     unsigned long long* trace;             // optional [nstrips][8] globaltimer stamps (developer tool) or nullptr
 };
@@ -87,22 +108,22 @@ __device__ __forceinline__ int4 ld_cg_int4(const int4* p)
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_cg_int4(int4* p, const int4& v)
-{
-    asm volatile("st.global.cg.v4.s32 [%0], {%1,%2,%3,%4};"
-                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 __device__ __forceinline__ void st_cs_int(int32_t* p, int v)
 {
     asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ int4 lds_volatile_int4(const int4* p)
+// shared-memory accesses by 32-bit shared address + compile-time byte offset
+template <int OFF>
+__device__ __forceinline__ int4 lds_volatile_int4(unsigned a)
 {
     int4 v;
-    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4+%5];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(OFF) : "memory");
     return v;
+}
+__device__ __forceinline__ int4 lds_volatile_int4(const int4* p)
+{
+    return lds_volatile_int4<0>((unsigned)__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ void sts_volatile_int4(int4* p, const int4& v)
 {
@@ -110,19 +131,36 @@ __device__ __forceinline__ void sts_volatile_int4(int4* p, const int4& v)
     asm volatile("st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4};"
                  ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-
 // stores under a PTX predicate: no branch, so a compute warp cannot diverge here
-__device__ __forceinline__ void sts_volatile_int4_if(int4* p, const int4& v, bool on)
+template <int OFF>
+__device__ __forceinline__ void sts_volatile_int4_if(unsigned a, const int4& v, int on)
 {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4}; }"
-                 ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((unsigned)on) : "memory");
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q st.volatile.shared.v4.s32 [%0+%6], {%1,%2,%3,%4}; }"
+                 ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(on), "n"(OFF) : "memory");
 }
-__device__ __forceinline__ void st_cg_int4_if(int4* p, const int4& v, bool on)
+template <int OFF>
+__device__ __forceinline__ void st_cg_int4_if(const int4* p, const int4& v, int on)
 {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.global.cg.v4.s32 [%0], {%1,%2,%3,%4}; }"
-                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((unsigned)on) : "memory");
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q st.global.cg.v4.s32 [%0+%6], {%1,%2,%3,%4}; }"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(on), "n"(OFF) : "memory");
 }
+template <int OFF>
+__device__ __forceinline__ void sts_int4(unsigned a, int x, int y, int z, int w)
+{
+    asm volatile("st.shared.v4.s32 [%0+%5], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ int lds_volatile_int(unsigned a)
+{
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile_int_if(unsigned a, int v, int on)
+{
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.volatile.shared.s32 [%0], %1; }" ::"r"(a), "r"(v), "r"(on) : "memory");
+}
+// a value the compiler / ptxas cannot rematerialise from the constant bank
+__device__ __forceinline__ int opaque(int x) { return __shfl_sync(0xffffffffu, x, 0); }
 
 // ---------------------------------------------------------------------------------
 // prep: packed copy of a -- word kAPad+j holds the characters of block j (columns
@@ -131,7 +169,8 @@ __device__ __forceinline__ void st_cg_int4_if(int4* p, const int4& v, bool on)
 // ---------------------------------------------------------------------------------
 __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m,
                             unsigned* __restrict__ a4, long long nwords,
-                            int* ticket, int* gmax, unsigned long long* key)
+                            int* ticket, int* gmax, unsigned long long* key,
+                            int* strip_max, long long nstrips)
 {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
@@ -146,124 +185,139 @@ __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m,
         }
         a4[w] = word;
     }
+    for (long long k = tid; k < nstrips; k += nth) strip_max[k] = 0;
     if (tid == 0) { *ticket = 0; *gmax = 0; *key = ~0ull; }
 }
 
 // ---------------------------------------------------------------------------------
 // compute warp
 // ---------------------------------------------------------------------------------
-#ifndef SWB_X_GATESLEEP
-#define SWB_X_GATESLEEP 100
-#endif
-
-// ---------------------------------------------------------------------------------
-// compute warp.  IMPORTANT: a compute warp never diverges -- every poll loop is executed
-// by all 32 lanes on a broadcast address.  (A lane-0-only spin loop leaves the warp split
-// and every following shuffle takes the divergent slow path: measured 8x slower steps.)
-// ---------------------------------------------------------------------------------
 struct Strip {
     int lane;
-    unsigned b4;
+    unsigned b4[kR];              // my rows' characters, replicated in the four bytes
     int sm, sx, gu, gl;
-    // dependency state (registers): block of the row above for this step, its last
-    // element of the previous step (diagonal of my first column), my last cell
-    int A0, A1, A2, A3, dgp, hl;
-    int s0, s1, s2, s3;           // substitution scores of this step's four cells
-    unsigned sa;                  // shared address of my next staging slot
-    unsigned sa_base;             // my row's 1 KB staging region
-    int4* ring_in;                // blocks of the row above my strip (tagged)
-    int4* ring_out;               // blocks of my last row, for the next strip of the band
-    int4* gout;                   // same, for the next band (global): slot of block t - lane
-    bool  has_in;                 // a strip above exists
-    bool  out_ring, out_glob;     // THIS LANE hands blocks on (lane 31 only): to the ring / to global
+    // dependency state (registers): block of the row above my first row for this step, its
+    // last element of the previous step (diagonal of my first column), the last cell of
+    // each of my rows
+    int A0, A1, A2, A3, dgp, hl[kR];
+    int s[kR][4];                 // substitution scores of this step's cells
+    unsigned sa;                  // shared address of my next staging slot (first row; row q at +q KB)
+    unsigned sa_base;             // my first row's 1 KB staging region
+    unsigned ring_in;             // shared address: blocks of the row above my strip (tagged)
+    unsigned ring_out;            // shared address: blocks of my last row, for the next strip of the band
+    const int4* gout;             // same, for the next band (global); block j of this group's first step
+    int   has_in;                 // a strip above exists
+    int   out_ring, out_glob;     // THIS LANE hands blocks on (lane 31 only): to the ring / to global
     int   jmax;
 
     __device__ __forceinline__ void scores(const unsigned aword)
     {
-        const unsigned x = aword ^ b4;
-        s0 = (x & 0x000000ffu) ? sx : sm;       // omp_smithW.c:394-399
-        s1 = (x & 0x0000ff00u) ? sx : sm;
-        s2 = (x & 0x00ff0000u) ? sx : sm;
-        s3 = (x & 0xff000000u) ? sx : sm;
+#pragma unroll
+        for (int q = 0; q < kR; ++q) {
+            const unsigned x = aword ^ b4[q];
+            s[q][0] = (x & 0x000000ffu) ? sx : sm;       // omp_smithW.c:394-399
+            s[q][1] = (x & 0x0000ff00u) ? sx : sm;
+            s[q][2] = (x & 0x00ff0000u) ? sx : sm;
+            s[q][3] = (x & 0xff000000u) ? sx : sm;
+        }
     }
 
     // one step.  EDGE: handles the zero column / not-yet-started lanes (first 4 groups) and
-    // the end of the producer's row (last groups).  next_word: packed characters of the
-    // NEXT step (its scores are computed in the shadow of the shuffles).
-    template <bool EDGE>
+    // the end of the producer's row (last groups).  I = step index inside the group
+    // (compile time: ring slots and the global hand-off are immediate offsets).
+    // next_word: packed characters of the NEXT step (its scores are computed in the shadow
+    // of the shuffles).  in_g / out_g: ring addresses of this group's first entries.
+    template <bool EDGE, int I>
     __device__ __forceinline__ void step(const int t, const unsigned next_word,
-                                         const int4* in_next, const int want_next, const int out_slot,
-                                         const int out_tag)
+                                         const unsigned in_g, const unsigned in_w, const int want, const int want_w,
+                                         const unsigned out_g, const unsigned out_w, const int otag, const int otag_w)
     {
+        constexpr bool LAST = (I == kGroup - 1);
         const int j = t - lane;
         const bool poll = has_in && (!EDGE || t + 1 <= jmax);
-        // block t+1 of the strip above (lane 0's row above for the next step): first try early
+        const int  wnt  = LAST ? want_w : want;
+        // block t+1 of the strip above (the row above lane 0's first row in the next step):
+        // first try early, it is needed only after the shuffles
         int4 v = make_int4(0, 0, 0, 0);
-        if (poll) v = lds_volatile_int4(in_next);
+        if (poll) v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
 
         // K = max(left+gap|LEFT, up+gap|UP, diag+s|DIAG, 0|NONE)     (omp_smithW.c:339-381)
-        const int p0 = __viaddmax_s32(dgp, s0, kTieNone);
-        const int p1 = __viaddmax_s32(A0, s1, kTieNone);
-        const int p2 = __viaddmax_s32(A1, s2, kTieNone);
-        const int p3 = __viaddmax_s32(A2, s3, kTieNone);
-        const int t0 = __viaddmax_s32(A0, gu, p0);
-        const int t1 = __viaddmax_s32(A1, gu, p1);
-        const int t2 = __viaddmax_s32(A2, gu, p2);
-        const int t3 = __viaddmax_s32(A3, gu, p3);
+        int u0 = A0, u1 = A1, u2 = A2, u3 = A3, dg = dgp;
         dgp = A3;
-        int k0 = __viaddmax_s32(hl, gl, t0);
-        if (EDGE) { if (j <= 0) k0 = kTieNone; }
-        const int h0 = k0 & ~15;
-        const int n0 = __shfl_up_sync(0xffffffffu, h0, 1);
-        int k1 = __viaddmax_s32(h0, gl, t1);
-        if (EDGE) { if (j < 0) k1 = kTieNone; }
-        const int h1 = k1 & ~15;
-        const int n1 = __shfl_up_sync(0xffffffffu, h1, 1);
-        int k2 = __viaddmax_s32(h1, gl, t2);
-        if (EDGE) { if (j < 0) k2 = kTieNone; }
-        const int h2 = k2 & ~15;
-        const int n2 = __shfl_up_sync(0xffffffffu, h2, 1);
-        int k3 = __viaddmax_s32(h2, gl, t3);
-        if (EDGE) { if (j < 0) k3 = kTieNone; }
-        const int h3 = k3 & ~15;
-        const int n3 = __shfl_up_sync(0xffffffffu, h3, 1);
-        hl = h3;
-
-        // ---------------- stage my packed block for the writer ----------------
-#ifndef SWB_X_NOSTAGE
-        asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(sa), "r"(k0), "r"(k1), "r"(k2), "r"(k3) : "memory");
-#endif
+        int n0, n1, n2, n3;
+#pragma unroll
+        for (int q = 0; q < kR; ++q) {
+            const int p0 = __viaddmax_s32(dg, s[q][0], kTieNone);
+            const int p1 = __viaddmax_s32(u0, s[q][1], kTieNone);
+            const int p2 = __viaddmax_s32(u1, s[q][2], kTieNone);
+            const int p3 = __viaddmax_s32(u2, s[q][3], kTieNone);
+            const int t0 = __viaddmax_s32(u0, gu, p0);
+            const int t1 = __viaddmax_s32(u1, gu, p1);
+            const int t2 = __viaddmax_s32(u2, gu, p2);
+            const int t3 = __viaddmax_s32(u3, gu, p3);
+            dg = hl[q];                                  // diagonal of the next row's first cell
+            int k0 = __viaddmax_s32(hl[q], gl, t0);
+            if (EDGE) { if (j <= 0) k0 = kTieNone; }
+            const int h0 = k0 & ~15;
+            if (q == kR - 1) n0 = __shfl_up_sync(0xffffffffu, h0, 1);
+            int k1 = __viaddmax_s32(h0, gl, t1);
+            if (EDGE) { if (j < 0) k1 = kTieNone; }
+            const int h1 = k1 & ~15;
+            if (q == kR - 1) n1 = __shfl_up_sync(0xffffffffu, h1, 1);
+            int k2 = __viaddmax_s32(h1, gl, t2);
+            if (EDGE) { if (j < 0) k2 = kTieNone; }
+            const int h2 = k2 & ~15;
+            if (q == kR - 1) n2 = __shfl_up_sync(0xffffffffu, h2, 1);
+            int k3 = __viaddmax_s32(h2, gl, t3);
+            if (EDGE) { if (j < 0) k3 = kTieNone; }
+            const int h3 = k3 & ~15;
+            if (q == kR - 1) n3 = __shfl_up_sync(0xffffffffu, h3, 1);
+            hl[q] = h3;
+            // stage the packed block of this row for the writers
+            if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
+            if (q == 1) sts_int4<kRowInts * 4>(sa, k0, k1, k2, k3);
+            if (q == 2) sts_int4<2 * kRowInts * 4>(sa, k0, k1, k2, k3);
+            if (q == 3) sts_int4<3 * kRowInts * 4>(sa, k0, k1, k2, k3);
+            u0 = h0; u1 = h1; u2 = h2; u3 = h3;          // the row above the next row
+        }
         sa = ((sa + 16u) & (unsigned)(kT * 16 - 1)) | sa_base;
 
         // ---------------- hand my last row to the next strip (lane 31 only) ----------------
         {
-            const bool started = !EDGE || j >= 0;
-            sts_volatile_int4_if(ring_out + out_slot, make_int4(h0 | out_tag, h1, h2, h3 | out_tag), out_ring && started);
-            st_cg_int4_if(gout, make_int4(h0 | 1, h1, h2, h3 | 1), out_glob && started);
-            gout += 1;                                            // block j+1 next step
+            const int started = (!EDGE || j >= 0) ? 1 : 0;
+            const int4 o = make_int4(u0 | (LAST ? otag_w : otag), u1, u2, u3);
+            if (LAST) sts_volatile_int4_if<0>(out_w, o, out_ring & started);
+            else      sts_volatile_int4_if<16 * I>(out_g, o, out_ring & started);
+            st_cg_int4_if<16 * I>(gout, o, out_glob & started);
         }
         // ---------------- scores of the next step ----------------
         scores(next_word);
 
         // ---------------- the row above, for the next step ----------------
         if (poll) {
-            int spins = 0;
-            while (((v.x & 3) != want_next) | ((v.w & 3) != want_next)) {
-                if (++spins > 32) __nanosleep(32);
-                v = lds_volatile_int4(in_next);
+            if (__builtin_expect((v.x & 3) != wnt, 0)) {
+                int spins = 0;
+                do {
+                    if (++spins > 64) __nanosleep(20);
+                    v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
+                } while ((v.x & 3) != wnt);
             }
         }
         const bool l0 = (lane == 0);
         A0 = l0 ? (v.x & ~15) : n0;
         A1 = l0 ? v.y : n1;
         A2 = l0 ? v.z : n2;
-        A3 = l0 ? (v.w & ~15) : n3;
+        A3 = l0 ? v.w : n3;
     }
 };
 
+// Flags live in shared memory and are passed as 32-bit shared addresses.  Ordering between
+// the staged data and its flag relies on the in-order shared-memory pipeline of one warp
+// (data STS, __syncwarp, flag STS; flag LDS, data LDS): a MEMBAR here waits for the writer's
+// outstanding GLOBAL stores as well and cost ~2500 clk per round.
 __device__ __forceinline__ void compute_strip(const FillParams& p, Strip& S, const unsigned* aw,
-                                              volatile int* staged, volatile int* drained,
-                                              volatile int* consumed_in, volatile int* consumed_out,
+                                              const unsigned staged, const unsigned drained,
+                                              const unsigned consumed_in, const unsigned consumed_out,
                                               const bool ring_consumer, const long long strip)
 {
     const int lane = S.lane;
@@ -274,162 +328,200 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip& S, con
 
     // first input block (block 0 -> ring index 32, epoch 0 -> tag 1); all lanes poll
     if (S.has_in) {
-        int4 v = lds_volatile_int4(S.ring_in + 32);
-        while (((v.x & 3) != 1) | ((v.w & 3) != 1)) { __nanosleep(SWB_X_GATESLEEP); v = lds_volatile_int4(S.ring_in + 32); }
-        if (lane == 0) { S.A0 = v.x & ~15; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w & ~15; }
+        int4 v = lds_volatile_int4<16 * 32>(S.ring_in);
+        while ((v.x & 3) != 1) { __nanosleep(SWB_X_GATESLEEP); v = lds_volatile_int4<16 * 32>(S.ring_in); }
+        if (lane == 0) { S.A0 = v.x & ~15; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w; }
     }
     trace_stamp(p, strip, 1, lane);
     S.scores(cur[0]);
 
     const int gtail = (p.jmax - 8) >> 3;          // groups g <= gtail: t+1 <= jmax for all their steps
+#ifdef SWB_X_GROUPTRACE
+    long long dbg_pre = 0, dbg_steps = 0, dbg_post = 0, dbg_n = 0, dbg_e_steps = 0, dbg_e_other = 0;
+#endif
     for (int g = 0; g < p.ngroups; ++g) {
+#ifndef SWB_X_GROUPTRACE
         if (g == 4) trace_stamp(p, strip, 2, lane);
         if (g == 8) trace_stamp(p, strip, 3, lane);
+#endif
         const int t0 = g * kGroup;
-        // ---- staging ring space: the writer must have drained the slots this group overwrites
+#ifdef SWB_X_GROUPTRACE
+        const long long gc0 = clock64();
+#endif
+        // ---- staging ring space: the writers must have drained the slots this group overwrites
+#ifndef SWB_X_NOWRITER
         if (g > kStageSlack) {
-            while (*drained < g - kStageSlack) { }
+#pragma unroll
+            for (int k = 0; k < kWriters; ++k) { while (lds_volatile_int(drained + 4u * k) < g - kStageSlack) { } }
         }
+#endif
         // ---- hand-off ring space (blocks up to t0+7-31 are written in this group)
-        if (ring_consumer && t0 - 80 > 0) { while (*consumed_out < t0 - 80) { } }
-        if (S.has_in && lane == 0) *consumed_in = t0;
+        if (ring_consumer && t0 - 80 > 0) { while (lds_volatile_int(consumed_out) < t0 - 80) { } }
+        sts_volatile_int_if(consumed_in, t0, S.has_in & (lane == 0 ? 1 : 0));
         // ---- sequence words of the next group
 #pragma unroll
         for (int i = 0; i < kGroup; ++i) nxt[i] = __ldg(aw + t0 + kGroup + i);
         cur[kGroup] = nxt[0];
 
         // consumer side: block t -> ring index (t+32)&63, epoch ((t+32)>>6)&1
-        const int4* in_base  = S.ring_in + ((t0 + 32) & (kRing - 1));
-        const int4* in_wrap  = S.ring_in + ((t0 + 40) & (kRing - 1));
+        const unsigned in_g  = S.ring_in + 16u * (unsigned)((t0 + 32) & (kRing - 1));
+        const unsigned in_w  = S.ring_in + 16u * (unsigned)((t0 + 40) & (kRing - 1));
         const int   want     = 1 + (((t0 + 32) >> 6) & 1);
         const int   want_w   = 1 + (((t0 + 40) >> 6) & 1);
-        // producer side: block t-31 -> ring index (t+1)&63, epoch ((t+1)>>6)&1
-        const int   ob       = (t0 & (kRing - 1)) + 1;
-        const int   ob_w     = (t0 + 8) & (kRing - 1);
+        // producer side: block t-31 -> ring index (t+1)&63, epoch ((t+1)>>6)&1 (= its (j+32) form)
+        const unsigned out_g = S.ring_out + 16u * (unsigned)((t0 & (kRing - 1)) + 1);
+        const unsigned out_w = S.ring_out + 16u * (unsigned)((t0 + 8) & (kRing - 1));
         const int   otag     = 1 + ((t0 >> 6) & 1);
         const int   otag_w   = 1 + (((t0 + 8) >> 6) & 1);
 
+#ifdef SWB_X_GROUPTRACE
+        const long long gc1 = clock64();
+#endif
+#define SWB_STEP(E, I) S.template step<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w)
         if (g >= 4 && g <= gtail) {
-#pragma unroll
-            for (int i = 0; i < kGroup; ++i) {
-                const bool last = (i == kGroup - 1);
-                S.template step<false>(t0 + i, cur[i + 1], last ? in_wrap : in_base + i + 1, last ? want_w : want,
-                                       last ? ob_w : ob + i, last ? otag_w : otag);
-            }
+            SWB_STEP(false, 0); SWB_STEP(false, 1); SWB_STEP(false, 2); SWB_STEP(false, 3);
+            SWB_STEP(false, 4); SWB_STEP(false, 5); SWB_STEP(false, 6); SWB_STEP(false, 7);
         } else {
-#pragma unroll
-            for (int i = 0; i < kGroup; ++i) {
-                const bool last = (i == kGroup - 1);
-                S.template step<true>(t0 + i, cur[i + 1], last ? in_wrap : in_base + i + 1, last ? want_w : want,
-                                      last ? ob_w : ob + i, last ? otag_w : otag);
-            }
+            SWB_STEP(true, 0); SWB_STEP(true, 1); SWB_STEP(true, 2); SWB_STEP(true, 3);
+            SWB_STEP(true, 4); SWB_STEP(true, 5); SWB_STEP(true, 6); SWB_STEP(true, 7);
         }
+#undef SWB_STEP
+#ifdef SWB_X_GROUPTRACE
+        const long long gc2 = clock64();
+#endif
+        S.gout += kGroup;
 #pragma unroll
         for (int i = 0; i < kGroup; ++i) cur[i] = nxt[i];
-        // ---- publish the staged group to the writer
+        // ---- publish the staged group to the writers
         __syncwarp();
-#ifndef SWB_X_NOFENCE
-        __threadfence_block();
+        sts_volatile_int_if(staged, g + 1, lane == 0 ? 1 : 0);
+#ifdef SWB_X_GROUPTRACE
+        { const long long gc3 = clock64();
+          if (g >= 8) { dbg_pre += gc1 - gc0; dbg_steps += gc2 - gc1; dbg_post += gc3 - gc2; ++dbg_n; }
+          else if (g < 4) { dbg_e_steps += gc2 - gc1; dbg_e_other += (gc1 - gc0) + (gc3 - gc2); } }
 #endif
-        if (lane == 0) *staged = g + 1;
     }
+#ifdef SWB_X_GROUPTRACE
+    if (p.trace && lane == 0) {
+        p.trace[strip * 8 + 2] = dbg_pre; p.trace[strip * 8 + 3] = dbg_steps; p.trace[strip * 8 + 4] = dbg_post;
+        p.trace[strip * 8 + 5] = dbg_n; p.trace[strip * 8 + 6] = dbg_e_steps; p.trace[strip * 8 + 7] = dbg_e_other;
+    }
+    return;
+#endif
     trace_stamp(p, strip, 4, lane);
 }
 
 // ---------------------------------------------------------------------------------
-// writer warp: drains the staging ring of one strip into H and P
+// writer warp: drains 32 rows of the staging ring of one strip into H and P
+//   sub = which 32 rows of the strip (0 .. kWriters-1)
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void writer_strip(const FillParams& p, const long long r0, const int lane,
-                                             const int* stage /* [32][kRowInts] */, int4* rowtab, int* ftab,
+__device__ __forceinline__ void writer_strip(const FillParams& p, const long long r0, const int sub, const int lane,
+                                             const int* stage /* this strip: [32*kR][kRowInts] */,
+                                             int4* rowtab,
                                              volatile int* staged, volatile int* drained, const long long strip)
 {
-    // per-row constants: round r flushes, for row l, the 32 columns 32r-E .. 32r-E+31 whose
+    // strip row rho = 32*sub + lane is computed by compute lane cl = rho / kR.
+    // per-row constants: round r flushes, for this row, the 32 columns 32r-E .. 32r-E+31 whose
     // first element sits on a 128-byte line of H (and P); E is the smallest such offset for
-    // which lane l has finished those columns by the end of compute group r
-    const long long row = r0 + lane;
+    // which lane cl has finished those columns by the end of compute group r
+    const int rho = 32 * sub + lane;
+    const int cl  = rho / kR;
+    const long long row = r0 + rho;
     const int ph = (int)((row * p.pitch) & 31);
-    const int d  = (lane + ((31 - ph) >> 2)) >> 3;
+    const int d  = (cl + ((31 - ph) >> 2)) >> 3;
     const int E  = 32 * d + ph;
     const long long G0 = row * p.pitch - E;                      // multiple of 32
-    const int F  = (8 * lane - E) & (kRowInts - 1);              // ring index of column c is (c + 8l) mod kRowInts
+    const int F  = (8 * cl - E) & (kRowInts - 1);                // ring index of column c is (c + 8*cl) mod kRowInts
     const unsigned long long hb = (unsigned long long)(p.H + G0);
-    const unsigned long long pb = (unsigned long long)(p.P + G0);
-    rowtab[lane] = make_int4((int)(unsigned)hb, (int)(unsigned)(hb >> 32), (int)(unsigned)pb, (int)(unsigned)(pb >> 32));
-    ftab[lane] = F;
-    ftab[32 + lane] = E;
+    rowtab[lane] = make_int4((int)(unsigned)hb, (int)(unsigned)(hb >> 32), F, E);
     const unsigned rowmask = __ballot_sync(0xffffffffu, row <= p.n);
     const int Emax = __reduce_max_sync(0xffffffffu, E);
     const int Emin = __reduce_min_sync(0xffffffffu, E);
     __syncwarp();
-
-#ifndef SWB_X_FINETRACE
-    trace_stamp(p, strip, 5, lane);
-#endif
+    const int* mystage = stage + (size_t)32 * sub * kRowInts;
 #ifdef SWB_X_NOWRITER
     return;
 #endif
+
     int mx = 0;
     const int rounds = p.ngroups + kDrainRounds;
     const int m = (int)p.m;
+    const long long pdelta = (long long)(p.P - p.H);              // P[i] sits pdelta ints after H[i]
+#ifdef SWB_X_WRITERTRACE
+    long long dw_wait = 0, dw_work = 0, dw_n = 0;
+#endif
     for (int r = 0; r < rounds; ++r) {
+#ifdef SWB_X_WRITERTRACE
+        const long long wc0 = clock64();
+#endif
         const int need = min(r + 1, p.ngroups);
         if (*staged < need) {
             int spins = 0;
-#ifndef SWB_X_WRITERSLEEP
-#define SWB_X_WRITERSLEEP 64
-#endif
             while (*staged < need) { if (++spins > 8) __nanosleep(SWB_X_WRITERSLEEP); }
         }
-#ifndef SWB_X_NOFENCE
-        __threadfence_block();
+        asm volatile("" ::: "memory");
+#ifdef SWB_X_WRITERTRACE
+        const long long wc1 = clock64();
 #endif
         const int v = 32 * r + lane;
         const bool interior = (rowmask == 0xffffffffu) && (32 * r - Emax >= 0) && (32 * r + 31 - Emin <= m);
         if (interior) {
-#pragma unroll 8
-            for (int l = 0; l < 32; ++l) {
-                const int4 tb = rowtab[l];
-                const int idx = (v + ftab[l]) & (kRowInts - 1);
-                const int k = stage[l * kRowInts + idx];
-                int32_t* hp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.y << 32) | (unsigned)tb.x) + v;
-                int32_t* pp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.w << 32) | (unsigned)tb.z) + v;
-                st_cs_int(hp, k >> 4);
-                st_cs_int(pp, k & 3);
-                mx = max(mx, k);
+            // batches of 8 rows: all table and data loads first, then the 16 stores
+#pragma unroll 1
+            for (int l0 = 0; l0 < 32; l0 += 8) {
+                int k[8]; int32_t* hp[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int4 tb = rowtab[l0 + i];
+                    hp[i] = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.y << 32) | (unsigned)tb.x) + v;
+                    k[i] = mystage[(l0 + i) * kRowInts + ((v + tb.z) & (kRowInts - 1))];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    __stcs(hp[i], k[i] >> 4);
+                    __stcs(hp[i] + pdelta, k[i] & 3);
+                    mx = max(mx, k[i]);
+                }
             }
         } else {
 #pragma unroll 2
             for (int l = 0; l < 32; ++l) {
                 const int4 tb = rowtab[l];
-                const int idx = (v + ftab[l]) & (kRowInts - 1);
-                const int c = v - ftab[32 + l];
+                const int idx = (v + tb.z) & (kRowInts - 1);
+                const int c = v - tb.w;
                 if (((rowmask >> l) & 1u) && c >= 0 && c <= m) {
-                    const int k = stage[l * kRowInts + idx];
+                    const int k = mystage[l * kRowInts + idx];
                     int32_t* hp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.y << 32) | (unsigned)tb.x) + v;
-                    int32_t* pp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.w << 32) | (unsigned)tb.z) + v;
-                    st_cs_int(hp, k >> 4);
-                    st_cs_int(pp, k & 3);
+                    __stcs(hp, k >> 4);
+                    __stcs(hp + pdelta, k & 3);
                     mx = max(mx, k);
                 }
             }
         }
         __syncwarp();
+        asm volatile("" ::: "memory");
         if (lane == 0) *drained = r + 1;
-    }
-    // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel)
-#ifndef SWB_X_FINETRACE
-    trace_stamp(p, strip, 6, lane);
+#ifdef SWB_X_WRITERTRACE
+        if (interior) { const long long wc2 = clock64(); dw_wait += wc1 - wc0; dw_work += wc2 - wc1; ++dw_n; }
 #endif
-    const int hm = __reduce_max_sync(0xffffffffu, mx) >> 4;
-    if (lane == 0) {
-        p.strip_max[strip] = hm;
-        if (hm > 0) atomicMax(p.gmax, hm);
     }
+#ifdef SWB_X_WRITERTRACE
+    if (p.trace && lane == 0 && sub == 0) { p.trace[strip * 8 + 5] = dw_wait; p.trace[strip * 8 + 6] = dw_work; p.trace[strip * 8 + 7] = dw_n; }
+#endif
+    // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel)
+    const int hm = __reduce_max_sync(0xffffffffu, mx) >> 4;
+    if (lane == 0 && hm > 0) {
+        atomicMax(p.strip_max + strip, hm);
+        atomicMax(p.gmax, hm);
+    }
+#if !defined(SWB_X_GROUPTRACE) && !defined(SWB_X_WRITERTRACE)
+    trace_stamp(p, strip, 5 + (sub & 1), lane);
+#endif
 }
 
 // ---------------------------------------------------------------------------------
 // loader warp: copies the tagged last row of the band above from global memory (L2)
-// into the first hand-off ring of this band
+// into the first hand-off ring of this band (same slot / epoch tag arithmetic)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void loader_band(const int4* src, const int nblocks, int4* ring, const int lane,
                                             volatile int* consumed)
@@ -442,12 +534,8 @@ __device__ __forceinline__ void loader_band(const int4* src, const int nblocks, 
         bool ok = false;
         if (j < limit) {
             const int4 v = ld_cg_int4(src + j);
-            ok = ((v.x & 3) == 1) && ((v.w & 3) == 1);
-            if (ok) {
-                const int tag = 1 + (((j + 32) >> 6) & 1);
-                sts_volatile_int4(ring + ((j + 32) & (kRing - 1)),
-                                  make_int4((v.x & ~15) | tag, v.y, v.z, (v.w & ~15) | tag));
-            }
+            ok = (v.x & 3) == 1 + (((j + 32) >> 6) & 1);
+            if (ok) sts_volatile_int4(ring + ((j + 32) & (kRing - 1)), v);
         }
         const unsigned mask = __ballot_sync(0xffffffffu, ok);
         const int lead = (mask == 0xffffffffu) ? 32 : (__ffs(~mask) - 1);
@@ -456,76 +544,102 @@ __device__ __forceinline__ void loader_band(const int4* src, const int nblocks, 
     }
 }
 
+// threads per block for wpc strips per band: rows of 4 warps; the 4-wpc serving schedulers
+// hold wpc*kWriters writers + 1 loader
+__host__ __device__ constexpr int fill_block_threads(int wpc)
+{
+    return 32 * 4 * ((wpc * kWriters + 1 + (4 - wpc) - 1) / (4 - wpc));
+}
+
 // ---------------------------------------------------------------------------------
-// The fill kernel.  grid = number of bands, block = 32*(2*wpc+1) threads:
-// warps [0,wpc) compute, [wpc,2wpc) write, warp 2wpc loads the band boundary.
-// dynamic smem = wpc * (32*kRowInts*4 + kRing*16 + 32*16 + 64*4) bytes.
+// The fill kernel.  grid = number of bands, block = fill_block_threads(wpc) threads (roles by
+// warp id, see below): wpc compute warps, wpc*kWriters writers, one loader of the band boundary.
+// dynamic smem = wpc * (kStripRows*kRowInts*4 + kRing*16 + kWriters*32*16) bytes.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * (2 * kMaxWpc + 1))
+__global__ void __launch_bounds__(1024)
 fill_kernel(const FillParams p)
 {
     extern __shared__ __align__(1024) int4 smem4[];
     __shared__ int s_band;
-    __shared__ int s_staged[kMaxWpc], s_drained[kMaxWpc], s_consumed[kMaxWpc + 1];
+    __shared__ int s_staged[kMaxWpc], s_drained[kMaxWpc * kWriters], s_consumed[kMaxWpc + 1];
 
     const int lane = threadIdx.x & 31;
-    const int w    = threadIdx.x >> 5;
+    const int wid  = threadIdx.x >> 5;
     const int wpc  = p.wpc;
+    // Warp roles by scheduler (a warp runs on SM sub-partition wid % 4).  A compute warp must
+    // not share its scheduler with another busy warp (measured: 190 -> 335 clk per step), so
+    // the compute warps take schedulers 0..wpc-1 (first row of warps) and the writers and the
+    // loader are spread over the other schedulers; the remaining warp slots exit at once.
+    const int sched = wid & 3, wrow = wid >> 2;
+    const int nserv = 4 - wpc;                                   // schedulers that serve writers / loader
+    const int nwriters = wpc * kWriters;
+    int role = -1;                                               // -1 idle, 0 compute, 1 writer, 2 loader
+    int w = 0;                                                   // compute: strip in the band; writer: writer index
+    if (sched < wpc) { if (wrow == 0) { role = 0; w = sched; } }
+    else {
+        const int slot = wrow * nserv + (sched - wpc);
+        if (slot < nwriters) { role = 1; w = slot; }
+        else if (slot == nwriters) role = 2;
+    }
 
-    int4* stage4  = smem4;                                       // [wpc][32][kT]
-    int4* rings   = stage4 + (size_t)wpc * 32 * kT;              // [wpc][kRing]
-    int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc][32]
-    int*  ftabs   = reinterpret_cast<int*>(rowtabs + (size_t)wpc * 32);   // [wpc][64]
+    int4* stage4  = smem4;                                       // [wpc][kStripRows][kT]
+    int4* rings   = stage4 + (size_t)wpc * kStripRows * kT;      // [wpc][kRing]
+    int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc*kWriters][32]
 
     if (threadIdx.x == 0) s_band = atomicAdd(p.ticket, 1);
-    if (threadIdx.x < kMaxWpc) { s_staged[threadIdx.x] = 0; s_drained[threadIdx.x] = 0; }
+    if (threadIdx.x < kMaxWpc) s_staged[threadIdx.x] = 0;
+    if (threadIdx.x < kMaxWpc * kWriters) s_drained[threadIdx.x] = 0;
     if (threadIdx.x <= kMaxWpc) s_consumed[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < wpc * kRing; i += blockDim.x) rings[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
     const int band = s_band;
-    const long long band_r0 = 1 + (long long)band * wpc * 32;
+    const long long band_r0 = 1 + (long long)band * wpc * kStripRows;
 
-    if (w < wpc) {
+    if (role == 0) {
         // ------------------------------------------------ compute
-        const long long r0 = band_r0 + 32LL * w;
+        const long long r0 = band_r0 + (long long)kStripRows * w;
         if (r0 > p.n) return;
         Strip S;
         S.lane = lane;
-        const long long row = r0 + lane;
-        S.b4 = (row <= p.n) ? (unsigned)p.b[row - 1] * 0x01010101u : 0u;
+#pragma unroll
+        for (int q = 0; q < kR; ++q) {
+            const long long row = r0 + kR * lane + q;
+            S.b4[q] = (row <= p.n) ? (unsigned)p.b[row - 1] * 0x01010101u : 0u;
+            S.hl[q] = 0;
+        }
         // keep the scoring constants in registers: a shuffle result is opaque to ptxas, which
         // otherwise re-reads them from the constant bank at the head of every step, on the
         // dependency chain
-        S.sm = __shfl_sync(0xffffffffu, p.s_match, 0);
-        S.sx = __shfl_sync(0xffffffffu, p.s_mismatch, 0);
-        S.gu = __shfl_sync(0xffffffffu, p.g_up, 0);
-        S.gl = __shfl_sync(0xffffffffu, p.g_left, 0);
-        S.A0 = S.A1 = S.A2 = S.A3 = 0; S.dgp = 0; S.hl = 0;
-        S.sa_base = (unsigned)__cvta_generic_to_shared(stage4 + ((size_t)w * 32 + lane) * kT);
+        S.sm = opaque(p.s_match); S.sx = opaque(p.s_mismatch); S.gu = opaque(p.g_up); S.gl = opaque(p.g_left);
+        S.A0 = S.A1 = S.A2 = S.A3 = 0; S.dgp = 0;
+        S.sa_base = (unsigned)__cvta_generic_to_shared(stage4 + ((size_t)w * kStripRows + (size_t)kR * lane) * kT);
         S.sa = S.sa_base + 16u * (unsigned)lane;                 // slot (t + lane) & (kT-1) at t = 0
-        S.ring_in  = rings + (size_t)w * kRing;
-        S.ring_out = rings + (size_t)(w + 1 < wpc ? w + 1 : w) * kRing;
+        S.ring_in  = (unsigned)__cvta_generic_to_shared(rings + (size_t)w * kRing);
+        S.ring_out = (unsigned)__cvta_generic_to_shared(rings + (size_t)(w + 1 < wpc ? w + 1 : w) * kRing);
         S.jmax = p.jmax;
-        S.has_in = (r0 > 1);
-        const bool next_row = (r0 + 32 <= p.n);                  // a strip below exists
+        S.has_in = opaque(r0 > 1 ? 1 : 0);
+        const bool next_row = (r0 + kStripRows <= p.n);          // a strip below exists
         const bool ring_consumer = next_row && (w + 1 < wpc);
-        S.out_ring = ring_consumer && lane == 31;
-        S.out_glob = next_row && (w + 1 == wpc) && lane == 31;
-        // block j = t - lane of step t goes to gout[j]; the pointer advances one block per step
-        // (only lane 31's copy is ever dereferenced, from t = 31 on)
+        S.out_ring = (ring_consumer && lane == 31) ? 1 : 0;
+        S.out_glob = (next_row && (w + 1 == wpc) && lane == 31) ? 1 : 0;
+        // block j = t - lane of step t goes to gout[j]: base of the group's first step, the
+        // step index is an immediate (only lane 31's copy is ever dereferenced, from t = 31 on)
         S.gout = p.boundary + (size_t)(next_row && (w + 1 == wpc) ? band : 0) * p.bstride - lane;
         const unsigned* aw = p.a4 + kAPad - lane;                // aw[t] = characters of block t - lane
-        compute_strip(p, S, aw, s_staged + w, s_drained + w, s_consumed + w, s_consumed + w + 1, ring_consumer,
-                      (r0 - 1) >> 5);
-    } else if (w < 2 * wpc) {
+        compute_strip(p, S, aw, (unsigned)__cvta_generic_to_shared(s_staged + w),
+                      (unsigned)__cvta_generic_to_shared(s_drained + w * kWriters),
+                      (unsigned)__cvta_generic_to_shared(s_consumed + w),
+                      (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, (r0 - 1) / kStripRows);
+    } else if (role == 1) {
         // ------------------------------------------------ writer
-        const int cw = w - wpc;
-        const long long r0 = band_r0 + 32LL * cw;
-        if (r0 > p.n) return;
-        writer_strip(p, r0, lane, reinterpret_cast<const int*>(stage4 + (size_t)cw * 32 * kT),
-                     rowtabs + (size_t)cw * 32, ftabs + (size_t)cw * 64, s_staged + cw, s_drained + cw,
-                     (r0 - 1) >> 5);
-    } else {
+        const int wi = w;                                        // writer index in the CTA
+        const int cw = wi / kWriters, sub = wi % kWriters;
+        const long long r0 = band_r0 + (long long)kStripRows * cw;
+        if (r0 > p.n) return;                                    // (a writer without valid rows still runs: it owns a drained flag)
+        writer_strip(p, r0, sub, lane, reinterpret_cast<const int*>(stage4 + (size_t)cw * kStripRows * kT),
+                     rowtabs + (size_t)wi * 32, s_staged + cw, s_drained + wi,
+                     (r0 - 1) / kStripRows);
+    } else if (role == 2) {
         // ------------------------------------------------ loader
         if (band == 0 || band_r0 > p.n) return;
         loader_band(p.boundary + (size_t)(band - 1) * p.bstride, p.jmax + 1, rings, lane, s_consumed);
@@ -547,7 +661,7 @@ __global__ void argmax_kernel(const int32_t* __restrict__ H, long long pitch, lo
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long r = 1 + warp; r <= n; r += nwarps) {
-        if (strip_max[(r - 1) >> 5] != g) continue;
+        if (strip_max[(r - 1) / kStripRows] != g) continue;
         const int32_t* Hr = H + r * pitch;
         for (long long j0 = 1; j0 <= m; j0 += 32) {
             const long long j = j0 + lane;

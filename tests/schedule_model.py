@@ -17,6 +17,9 @@ import numpy as np
 
 TIE_NONE, TIE_DIAG, TIE_UP, TIE_LEFT = 8, 7, 5, 2
 KT = 64
+KR = 2                 # adjacent rows per lane (SWB_ROWS_PER_LANE)
+STRIP_ROWS = 32 * KR
+WRITERS = KR
 ROW_INTS = 4 * KT
 RING = 64
 GROUP = 8
@@ -41,7 +44,7 @@ def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed
     ngroups = (jmax + 1 + 31 + GROUP - 1) // GROUP
     gtail = (jmax - 8) >> 3
     bstride = ngroups * GROUP
-    strips = (n + 31) // 32
+    strips = (n + STRIP_ROWS - 1) // STRIP_ROWS
     nbands = (strips + wpc - 1) // wpc
     lane = np.arange(32)
     rng = np.random.default_rng(seed)
@@ -67,33 +70,35 @@ def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed
         def __init__(self, s):
             self.s = s
             self.band, self.w = divmod(s, wpc)
-            self.r0 = 1 + 32 * s
-            rows = self.r0 + lane
-            self.bch = np.where(rows <= n, b[np.minimum(rows, n) - 1], 0)
+            self.r0 = 1 + STRIP_ROWS * s
+            self.bch = []
+            for q in range(KR):
+                rows = self.r0 + KR * lane + q
+                self.bch.append(np.where(rows <= n, b[np.minimum(rows, n) - 1], 0))
             self.A = np.zeros((32, 4), dtype=np.int64)
             self.dgp = np.zeros(32, dtype=np.int64)
-            self.hl = np.zeros(32, dtype=np.int64)
+            self.hl = [np.zeros(32, dtype=np.int64) for _ in range(KR)]
             self.g = 0
             self.started = False
-            self.stage = np.full((32, ROW_INTS), POISON, dtype=np.int64)
+            self.stage = np.full((STRIP_ROWS, ROW_INTS), POISON, dtype=np.int64)
             self.ring = np.zeros((RING, 4), dtype=np.int64)                  # my INPUT ring
             self.staged = 0
-            self.drained = 0
+            self.drained = [0] * WRITERS
             self.consumed = 0                                                  # blocks of my input ring I am done with
             self.has_in = self.r0 > 1
-            nxt = self.r0 + 32 <= n
+            nxt = self.r0 + STRIP_ROWS <= n
             self.out = 0 if not nxt else (1 if self.w + 1 < wpc else 2)
 
         def ring_valid(self, j):
             e = self.ring[(j + 32) & (RING - 1)]
             want = 1 + (((j + 32) >> 6) & 1)
-            return (e[0] & 3) == want and (e[3] & 3) == want
+            return (e[0] & 3) == want
 
         def runnable(self):
             g = self.g
             if g >= ngroups:
                 return False
-            if g > STAGE_SLACK and self.drained < g - STAGE_SLACK:
+            if g > STAGE_SLACK and min(self.drained) < g - STAGE_SLACK:
                 return False
             t0 = g * GROUP
             if self.out == 1 and t0 - 80 > 0 and comp[self.s + 1].consumed < t0 - 80:
@@ -109,7 +114,6 @@ def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed
             assert self.ring_valid(j)
             e = self.ring[(j + 32) & (RING - 1)].copy()
             e[0] &= ~15
-            e[3] &= ~15
             self.A[0] = e
 
         def run(self):
@@ -124,39 +128,42 @@ def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed
                 t = t0 + i
                 j = t - lane
                 ch = achars(j)
-                s = np.where(ch == self.bch[:, None], sm, sx)
-                A, hl = self.A, self.hl.copy()
-                k = np.zeros((32, 4), dtype=np.int64)
-                h = np.zeros((32, 4), dtype=np.int64)
-                dg = self.dgp
-                for e in range(4):
-                    ke = np.maximum(np.maximum(hl + gl, A[:, e] + gu), np.maximum(dg + s[:, e], TIE_NONE))
-                    if not fast:
-                        ke = np.where((j < 0) | ((j == 0) & (e == 0)), TIE_NONE, ke)
-                    else:
-                        assert (j >= 1).all()
-                    k[:, e] = ke
-                    h[:, e] = ke & ~15
-                    hl = h[:, e]
-                    dg = A[:, e]
-                self.hl = hl
-                self.dgp = A[:, 3].copy()
-                # stage: lane l, slot (t + l) & (KT-1)
+                u = self.A.copy()
+                dg = self.dgp.copy()
+                self.dgp = self.A[:, 3].copy()
                 slot = (t + lane) & (KT - 1)
-                for e in range(4):
-                    self.stage[lane, 4 * slot + e] = k[:, e]
+                for q in range(KR):
+                    sc = np.where(ch == self.bch[q][:, None], sm, sx)
+                    hl = self.hl[q].copy()
+                    dgn = self.hl[q].copy()                      # diagonal of the next row's first cell
+                    k = np.zeros((32, 4), dtype=np.int64)
+                    h = np.zeros((32, 4), dtype=np.int64)
+                    for e in range(4):
+                        ke = np.maximum(np.maximum(hl + gl, u[:, e] + gu), np.maximum(dg + sc[:, e], TIE_NONE))
+                        if not fast:
+                            ke = np.where((j < 0) | ((j == 0) & (e == 0)), TIE_NONE, ke)
+                        else:
+                            assert (j >= 1).all()
+                        k[:, e] = ke
+                        h[:, e] = ke & ~15
+                        hl = h[:, e]
+                        dg = u[:, e]
+                    self.hl[q] = hl
+                    dg = dgn
+                    u = h
+                    # stage: strip row KR*lane + q, slot (t + lane) & (KT-1)
+                    for e in range(4):
+                        self.stage[KR * lane + q, 4 * slot + e] = k[:, e]
+                h = u                                             # the lane's last row
                 # hand-off of lane 31
                 j31 = t - 31
                 if self.out and (fast or j31 >= 0):
                     blk = h[31].copy()
+                    tag = 1 + (((t + 1) >> 6) & 1)
+                    blk[0] |= tag
                     if self.out == 1:
-                        tag = 1 + (((t + 1) >> 6) & 1)
-                        blk[0] |= tag
-                        blk[3] |= tag
                         comp[self.s + 1].ring[(t + 1) & (RING - 1)] = blk
                     else:
-                        blk[0] |= 1
-                        blk[3] |= 1
                         boundary[self.band, j31] = blk
                 # row above for the next step
                 newA = np.zeros((32, 4), dtype=np.int64)
@@ -169,17 +176,20 @@ def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed
             self.staged = self.g
 
     class Writer:
-        def __init__(self, s):
-            self.s = s
+        def __init__(self, s, sub):
+            self.s, self.sub = s, sub
             self.c = comp[s]
             r0 = self.c.r0
-            rows = r0 + lane
+            rho = 32 * sub + lane
+            self.rho = rho
+            cl = rho // KR
+            rows = r0 + rho
             ph = (rows * pitch) & 31
-            d = (lane + ((31 - ph) >> 2)) >> 3
+            d = (cl + ((31 - ph) >> 2)) >> 3
             self.E = 32 * d + ph
             self.G0 = rows * pitch - self.E
             assert (self.G0 % 32 == 0).all()
-            self.F = (8 * lane - self.E) & (ROW_INTS - 1)
+            self.F = (8 * cl - self.E) & (ROW_INTS - 1)
             self.rowok = rows <= n
             self.r = 0
             self.mx = 0
@@ -198,7 +208,7 @@ def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed
                 ok = np.full(32, True) if interior else (self.rowok[l] & (c >= 0) & (c <= m))
                 if interior:
                     assert self.rowok[l] and (c >= 0).all() and (c <= m).all()
-                k = self.c.stage[l, idx]
+                k = self.c.stage[self.rho[l], idx]
                 gi = self.G0[l] + v
                 kk = k[ok]
                 assert (kk != POISON).all(), "writer read a slot that was never written"
@@ -208,9 +218,9 @@ def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed
                 if kk.size:
                     self.mx = max(self.mx, int(kk.max()))
             self.r += 1
-            self.c.drained = self.r
+            self.c.drained[self.sub] = self.r
             if self.r == self.rounds:
-                strip_max[self.s] = self.mx >> 4
+                strip_max[self.s] = max(strip_max[self.s], self.mx >> 4)
 
     class Loader:
         def __init__(self, band):
@@ -224,7 +234,7 @@ def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed
             src = boundary[self.band - 1]
             n_ok = 0
             for j in range(self.base, min(limit, self.base + 32)):
-                if (src[j, 0] & 3) == 1 and (src[j, 3] & 3) == 1:
+                if (src[j, 0] & 3) == 1 + (((j + 32) >> 6) & 1):
                     n_ok += 1
                 else:
                     break
@@ -236,15 +246,11 @@ def fill_model(a, b, scoring=(3, -3, -2), wpc=2, pitch=None, policy="lazy", seed
         def run(self):
             src = boundary[self.band - 1]
             for j in range(self.base, self.base + self.avail()):
-                tag = 1 + (((j + 32) >> 6) & 1)
-                blk = src[j].copy()
-                blk[0] = (blk[0] & ~15) | tag
-                blk[3] = (blk[3] & ~15) | tag
-                self.c.ring[(j + 32) & (RING - 1)] = blk
+                self.c.ring[(j + 32) & (RING - 1)] = src[j].copy()
                 self.base += 1
 
     comp = [Compute(s) for s in range(strips)]
-    writers = [Writer(s) for s in range(strips)]
+    writers = [Writer(s, sub) for s in range(strips) for sub in range(WRITERS)]
     loaders = [Loader(bd) for bd in range(1, nbands)]
 
     def pick():

@@ -76,5 +76,6 @@ def test_schedule_model_reproduces_oracle(oracle, m, n, wpc, pitch, policy):
     H, P, _ = oracle.fill(a, b)
     Hm, Pm, smax = fill_model(a, b, wpc=wpc, pitch=pitch, policy=policy, seed=m + n)
     assert (Hm == H).all() and (Pm == P).all()
-    want = [H[1 + 32 * s: 33 + 32 * s].max() for s in range((n + 31) // 32)]
+    from schedule_model import STRIP_ROWS
+    want = [H[1 + STRIP_ROWS * s: 1 + STRIP_ROWS * (s + 1)].max() for s in range((n + STRIP_ROWS - 1) // STRIP_ROWS)]
     assert list(smax) == want

@@ -14,7 +14,7 @@ dev = torch.device("cuda:0")
 a, b = swb.generate(42, cols, rows)
 a_d = torch.frombuffer(bytearray(a), dtype=torch.uint8).to(dev); b_d = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
 dH = torch.empty((rows + 1) * (cols + 1), dtype=torch.int32, device=dev); dP = torch.empty_like(dH)
-strips = (rows + 31) // 32
+strips = (rows + 63) // 64
 for it in range(2):
     tr = torch.zeros(strips * 8, dtype=torch.int64, device=dev)
     swb.fill_async(a_d, cols, b_d, rows, dH, dP, cols + 1, None, None, warps_per_band=args.wpc, trace=tr)
@@ -22,7 +22,7 @@ for it in range(2):
 t = tr.view(strips, 8).cpu().numpy().astype("float64")
 t0 = t[:, 0].min()
 t = (t - t0) / 1000.0
-names = ["enter", "gate", "g4", "g8", "end", "w_start", "w_end"]
+names = ["enter", "gate", "g4", "g8", "end", "w0_end", "w1_end"]
 print("strip " + " ".join(f"{n:>9s}" for n in names) + "   (us since first entry)")
 for s in list(range(0, min(strips, 12))) + list(range(strips // 2, strips // 2 + 4)) + list(range(strips - 3, strips)):
     print(f"{s:5d} " + " ".join(f"{t[s, k]:9.1f}" for k in range(7)))

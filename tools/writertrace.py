@@ -1,22 +1,21 @@
 import importlib, sys, torch, numpy as np
 sys.path.insert(0, '.')
 swb = importlib.import_module("smith-waterman_b200")
-cols=rows=4096
+cols=rows=8192
 wpc=int(sys.argv[1]) if len(sys.argv)>1 else 2
+SR=64
 dev=torch.device("cuda:0")
 a,b=swb.generate(42,cols,rows)
 a_d=torch.frombuffer(bytearray(a),dtype=torch.uint8).to(dev); b_d=torch.frombuffer(bytearray(b),dtype=torch.uint8).to(dev)
 dH=torch.empty((rows+1)*(cols+1),dtype=torch.int32,device=dev); dP=torch.empty_like(dH)
-strips=(rows+31)//32
+strips=(rows+SR-1)//SR
 for it in range(2):
     tr=torch.zeros(strips*8,dtype=torch.int64,device=dev)
     swb.fill_async(a_d,cols,b_d,rows,dH,dP,cols+1,None,None,warps_per_band=wpc,trace=tr)
     torch.cuda.synchronize()
-t=tr.view(strips,8).cpu().numpy()
-print("strip | steps 0-31: clk/step wait/step spins | steps 32-63: ... | steps 64-575: ...")
-for s in list(range(8))+[60,61,62,63]:
-    r=t[s]
-    def f(a0,a1,b0,b1,n):
-        st=(a1-a0)/n; w=(b1//1000-b0//1000)/n; sp=(b1%1000-b0%1000)
-        return f"{st:7.1f} {w:6.1f} {sp:4d}"
-    print(f"{s:3d} | "+f(0,r[2],0,r[3],32)+" | "+f(r[2],r[4],r[3],r[5],32)+" | "+f(r[4],r[6],r[5],r[7],512))
+t=tr.view(strips,8).cpu().numpy().astype(float)
+n=np.maximum(t[:,7],1)
+print("writer 0 of each strip, interior rounds: wait clk/round, work clk/round")
+for s in list(range(4))+[strips//2, strips//2+1, strips-2, strips-1]:
+    print(s, round(t[s,5]/n[s],1), round(t[s,6]/n[s],1), int(n[s]))
+print("mean wait %.1f work %.1f" % ((t[:,5]/n).mean(), (t[:,6]/n).mean()))
