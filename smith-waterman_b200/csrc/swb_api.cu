@@ -80,7 +80,7 @@ size_t fill_smem_bytes(int wpc)
 
 int pick_wpc(int64_t n, const swb_tuning* tuning)
 {
-    int wpc = 1;
+    int wpc = 2;
     if (const char* e = std::getenv("SWB_WPC")) wpc = std::atoi(e);
     if (tuning && tuning->warps_per_band > 0) wpc = tuning->warps_per_band;
     wpc = std::max(1, std::min(wpc, swb::kMaxWpc));
@@ -291,7 +291,9 @@ int swb_backtrack_async(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    swb::backtrack_kernel<<<1, 32, 0, st>>>(dP, pitch, maxPos, reinterpret_cast<const long long*>(d_maxPos),
+    const int bt_smem = (2 * (swb::kBtPad + swb::kBtBandInts) + 2 * swb::kBtList) * (int)sizeof(int);
+    SWB_CUDA(cudaFuncSetAttribute(swb::backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt_smem));
+    swb::backtrack_kernel<<<1, swb::kBtThreads, bt_smem, st>>>(dP, pitch, maxPos, reinterpret_cast<const long long*>(d_maxPos),
                                             reinterpret_cast<long long*>(d_pathLen));
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;

@@ -38,6 +38,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #ifndef SWB_X_GATESLEEP
 #define SWB_X_GATESLEEP 100
@@ -62,7 +63,8 @@ constexpr int kRowInts  = 4 * kT;      // ints per row of the staging ring
 constexpr int kRing     = 64;          // hand-off ring capacity in blocks (power of two)
 constexpr int kGroup    = 8;           // steps per synchronisation group
 constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
-constexpr int kMaxWpc   = 3;           // strips per band (CTA) upper bound (one scheduler must serve the writers)
+constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: compute warps on schedulers 0..wpc-1,
+                                       // writers + loader on the others
 constexpr int kDrainRounds = 2;        // writer rounds after the last compute group
 // writer round r reads steps [8r-8, 8r+7]; compute group g overwrites the slots of group
 // g - kT/8, which rounds <= g - kT/8 + 1 read: g may start once that many rounds are done
@@ -158,6 +160,16 @@ __device__ __forceinline__ int lds_volatile_int(unsigned a)
 __device__ __forceinline__ void sts_volatile_int_if(unsigned a, int v, int on)
 {
     asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.volatile.shared.s32 [%0], %1; }" ::"r"(a), "r"(v), "r"(on) : "memory");
+}
+// Wait until the shared-memory word at `a` is >= want.  The first check sits outside the
+// loop: ptxas puts a YIELD into every loop with a volatile load, and a YIELD on the straight
+// path costs ~100 clk even when the flag is already set.
+__device__ __forceinline__ void spin_until_ge(unsigned a, int want)
+{
+#ifdef SWB_X_SPINFIRST
+    if (__builtin_expect(lds_volatile_int(a) >= want, 1)) return;
+#endif
+    while (lds_volatile_int(a) < want) { }
 }
 // a value the compiler / ptxas cannot rematerialise from the constant bank
 __device__ __forceinline__ int opaque(int x) { return __shfl_sync(0xffffffffu, x, 0); }
@@ -294,6 +306,9 @@ struct Strip {
         scores(next_word);
 
         // ---------------- the row above, for the next step ----------------
+        // (Tried: after a miss, also wait for the block after it so that the strip runs one
+        // step behind its producer and the early load always hits.  Misses became rare but the
+        // fill got 5% slower -- one more step of lag per strip -- so the plain poll stays.)
         if (poll) {
             if (__builtin_expect((v.x & 3) != wnt, 0)) {
                 int spins = 0;
@@ -352,11 +367,11 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip& S, con
 #ifndef SWB_X_NOWRITER
         if (g > kStageSlack) {
 #pragma unroll
-            for (int k = 0; k < kWriters; ++k) { while (lds_volatile_int(drained + 4u * k) < g - kStageSlack) { } }
+            for (int k = 0; k < kWriters; ++k) spin_until_ge(drained + 4u * k, g - kStageSlack);
         }
 #endif
         // ---- hand-off ring space (blocks up to t0+7-31 are written in this group)
-        if (ring_consumer && t0 - 80 > 0) { while (lds_volatile_int(consumed_out) < t0 - 80) { } }
+        if (ring_consumer && t0 - 80 > 0) spin_until_ge(consumed_out, t0 - 80);
         sts_volatile_int_if(consumed_in, t0, S.has_in & (lane == 0 ? 1 : 0));
         // ---- sequence words of the next group
 #pragma unroll
@@ -478,8 +493,12 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
+#ifndef SWB_X_NOSTG
                     __stcs(hp[i], k[i] >> 4);
                     __stcs(hp[i] + pdelta, k[i] & 3);
+#else
+                    if (k[i] == 0x7ffffff1) __stcs(hp[i], k[i] >> 4);
+#endif
                     mx = max(mx, k[i]);
                 }
             }
@@ -556,7 +575,7 @@ __host__ __device__ constexpr int fill_block_threads(int wpc)
 // warp id, see below): wpc compute warps, wpc*kWriters writers, one loader of the band boundary.
 // dynamic smem = wpc * (kStripRows*kRowInts*4 + kRing*16 + kWriters*32*16) bytes.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(fill_block_threads(kMaxWpc))
 fill_kernel(const FillParams p)
 {
     extern __shared__ __align__(1024) int4 smem4[];
@@ -660,21 +679,31 @@ __global__ void argmax_kernel(const int32_t* __restrict__ H, long long pitch, lo
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long r = 1 + warp; r <= n; r += nwarps) {
-        if (strip_max[(r - 1) / kStripRows] != g) continue;
-        const int32_t* Hr = H + r * pitch;
-        for (long long j0 = 1; j0 <= m; j0 += 32) {
-            const long long j = j0 + lane;
-            const int v = (j <= m) ? Hr[j] : -1;
-            const unsigned hit = __ballot_sync(0xffffffffu, v == g);
-            if (hit) {
-                if (lane == 0) {
-                    const long long jj = j0 + (__ffs(hit) - 1);
-                    const unsigned long long k = ((unsigned long long)(r + jj) << 32) |
-                                                 (unsigned long long)(0xffffffffu - (unsigned)r);
-                    atomicMin(key, k);
+    constexpr int kChunk = 1024;                                   // columns per work item
+    const long long nchunks = (m + kChunk - 1) / kChunk;
+    const long long nstrips = (n + kStripRows - 1) / kStripRows;
+    // work item = (strip, row in strip, column chunk); strips that do not attain the maximum are skipped whole
+    for (long long st = 0; st < nstrips; ++st) {
+        if (strip_max[st] != g) continue;
+        const long long items = (long long)kStripRows * nchunks;
+        for (long long it = warp; it < items; it += nwarps) {
+            const long long r = st * kStripRows + 1 + it / nchunks;
+            if (r > n) continue;
+            const long long c0 = 1 + (it % nchunks) * kChunk;
+            const int32_t* Hr = H + r * pitch;
+            for (long long j0 = c0; j0 < c0 + kChunk && j0 <= m; j0 += 32) {
+                const long long j = j0 + lane;
+                const int v = (j <= m) ? Hr[j] : -1;
+                const unsigned hit = __ballot_sync(0xffffffffu, v == g);
+                if (hit) {
+                    if (lane == 0) {
+                        const long long jj = j0 + (__ffs(hit) - 1);
+                        const unsigned long long k = ((unsigned long long)(r + jj) << 32) |
+                                                     (unsigned long long)(0xffffffffu - (unsigned)r);
+                        atomicMin(key, k);
+                    }
+                    break;      // later columns of this row lie on later anti-diagonals
                 }
-                break;      // later columns of this row lie on later anti-diagonals
             }
         }
     }
@@ -697,48 +726,207 @@ __global__ void finalize_kernel(const unsigned long long* key, const int* gmax, 
 
 // ---------------------------------------------------------------------------------
 // backtrack (omp_smithW.c:405-420): follow P from maxPos until a NONE cell, negating
-// the path in place.  One warp: the 32x32 window of P ending at the current cell is
-// fetched with 32 coalesced loads in flight, lane 0 walks inside it (>= 32 moves per
-// window), so the serial chain pays one global round trip per window, not per cell.
+// the path in place.  The chain is serial, so the kernel hides the HBM latency and keeps
+// the per-cell dependency chain minimal (one shared-memory load + two ALU ops).
+// The path moves up-left along a diagonal with small drift, so P is read in diagonal
+// BANDS: 128 rows, and in row r the 128 columns around c0 - (i0 - r) where (i0, c0) is the
+// cell the band was entered at.  While lane 0 of warp 0 walks the path inside the current
+// band (in shared memory; it only records the visited band indices), warps 1..7 negate the
+// cells of the previous band's path in global memory and prefetch the band that continues
+// the diagonal with 16-byte cp.async (a band row is staged from the aligned global element
+// at or before its first column; the walker tracks the row's 0..3 element shift off the
+// dependency chain).  4-byte copies kept the LSU so busy that every load of the walker
+// took ~190 clk.  The first and last column of a band and the row above it hold the marker
+// 4: stepping on it ends the walk in this band.  If the walk leaves a band sideways, or
+// enters the next one too far off centre, a band centred on the current cell is fetched
+// instead.  One CTA of 256 threads, two band buffers (2 x 66 KB).
 // ---------------------------------------------------------------------------------
-__global__ void backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
-                                 const long long* d_maxPos, long long* d_pathLen)
+constexpr int kBtRows = 128;
+constexpr int kBtCols = 128;
+constexpr int kBtRS = 132;                           // staged ints per band row: 33 aligned 16-byte chunks
+constexpr int kBtThreads = 256;
+constexpr int kBtFetchers = kBtThreads - 32;
+constexpr int kBtBandInts = kBtRows * kBtRS;
+constexpr int kBtPad = 160;                          // ints before each band = the marker row above it
+constexpr int kBtList = 512;                         // a band holds at most 128 + 126 path cells
+constexpr int kBtMark = 4;
+
+// global index of band column 0 of band row rr, for the band entered at (i0, c0) (its cell (127, 64))
+__device__ __forceinline__ long long bt_row_start(long long i0, long long c0, long long pitch, int rr, long long& r)
 {
-    __shared__ int win[32][33];
-    const int lane = threadIdx.x;
-    long long pos = d_maxPos ? *d_maxPos : maxPos_arg;
-    long long len = 0;
-    if (pos > 0) {
-        long long i = pos / pitch, j = pos % pitch;
-        while (true) {
-            const long long wi0 = i - 31, wj0 = j - 31;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-                const long long gi = wi0 + rr, gj = wj0 + lane;
-                win[rr][lane] = (gi >= 0 && gj >= 0) ? P[gi * pitch + gj] : 0;
-            }
-            __syncwarp();
-            int done = 0, li = 31, lj = 31;
-            if (lane == 0) {
-                while (li >= 0 && lj >= 0) {
-                    const int pv = win[li][lj];
-                    if (pv == 0) { done = 1; break; }                 // NONE ends the path (:419)
-                    P[(wi0 + li) * pitch + (wj0 + lj)] = -pv;        // *= PATH (:417)
-                    ++len;
-                    if (pv == 3)      { --li; --lj; }                // DIAGONAL (:410)
-                    else if (pv == 1) { --li; }                      // UP (:412)
-                    else              { --lj; }                      // LEFT (:414)
-                }
-            }
-            done = __shfl_sync(0xffffffffu, done, 0);
-            li = __shfl_sync(0xffffffffu, li, 0);
-            lj = __shfl_sync(0xffffffffu, lj, 0);
-            i = wi0 + li; j = wj0 + lj;
-            __syncwarp();
-            if (done || i < 0 || j < 0) break;
+    r = i0 - (kBtRows - 1) + rr;
+    return r * pitch + (c0 - (i0 - r) - kBtCols / 2);
+}
+
+// prefetch warps only.  limit = number of valid ints of P the kernel may read.
+__device__ __forceinline__ void bt_fetch_band(int* buf, const int32_t* P, long long pitch, long long limit,
+                                              long long i0, long long c0)
+{
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
+    const int tid = threadIdx.x - 32;
+    for (int e = tid; e < kBtRows * (kBtRS / 4); e += kBtFetchers) {
+        const int rr = e / (kBtRS / 4), ch = e % (kBtRS / 4);
+        long long r;
+        const long long s = bt_row_start(i0, c0, pitch, rr, r);
+        const long long g0 = (s & ~3LL) + 4 * ch;                 // aligned global index of this chunk
+        int* dst = buf + rr * kBtRS + 4 * ch;
+        if (r >= 0 && g0 >= 0 && g0 + 4 <= limit) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 4u * (unsigned)(rr * kBtRS + 4 * ch)), "l"(P + g0) : "memory");
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = (r >= 0 && g0 + k >= 0 && g0 + k < limit) ? P[g0 + k] : 0;
         }
     }
-    if (lane == 0 && d_pathLen) *d_pathLen = len;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kBtFetchers) : "memory");
+    // marker columns (band columns 0 and 127), over the landed data
+    for (int e = tid; e < 2 * kBtRows; e += kBtFetchers) {
+        const int rr = e >> 1;
+        long long r;
+        const int sh = (int)(bt_row_start(i0, c0, pitch, rr, r) & 3);
+        buf[rr * kBtRS + sh + ((e & 1) ? kBtCols - 1 : 0)] = kBtMark;
+    }
+}
+
+// negate the recorded path cells of a finished band in global memory (*= PATH, :417)
+__device__ __forceinline__ void bt_writeback(const int* buf, const int* list, int count, int32_t* P, long long pitch,
+                                             long long i0, long long c0)
+{
+    const int tid = threadIdx.x - 32;
+    for (int e = tid; e < count; e += kBtFetchers) {
+        const int a = list[e];
+        const int rr = a / kBtRS;
+        long long r;
+        const long long s = bt_row_start(i0, c0, pitch, rr, r);
+        P[s + (a - rr * kBtRS - (int)(s & 3))] = -buf[a];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBtFetchers) : "memory");   // all of it read before the buffer is reused
+}
+
+__global__ void __launch_bounds__(kBtThreads)
+backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
+                 const long long* d_maxPos, long long* d_pathLen)
+{
+    extern __shared__ __align__(16) int bt_smem[];      // 2 x (pad + 128x132 ints), then 2 lists
+    __shared__ long long s_len;
+    __shared__ int s_done, s_a, s_count[2];
+    const long long pos = d_maxPos ? *d_maxPos : maxPos_arg;
+    if (pos <= 0) { if (threadIdx.x == 0 && d_pathLen) *d_pathLen = 0; return; }
+    long long i = pos / pitch, j = pos % pitch;         // current cell
+    // the path only moves up and left: nothing after the end of the start row is ever needed (or read)
+    const long long limit = (i + 1) * pitch;
+    const bool walker = threadIdx.x == 0, fetcher = threadIdx.x >= 32;
+    auto bandbuf = [&](int b) { return bt_smem + b * (kBtPad + kBtBandInts) + kBtPad; };
+    auto listbuf = [&](int b) { return bt_smem + 2 * (kBtPad + kBtBandInts) + b * kBtList; };
+    if (walker) { s_len = 0; s_done = 0; s_count[0] = 0; s_count[1] = 0; }
+    for (int e = threadIdx.x; e < 2 * kBtPad; e += kBtThreads)
+        bt_smem[(e / kBtPad) * (kBtPad + kBtBandInts) + e % kBtPad] = kBtMark;
+    int cur = 0;
+    long long bi = i, bc = j;                           // entry cell of the band in buffer `cur`
+    long long pbi = 0, pbc = 0;                         // entry cell of the previous band (buffer cur^1) to write back
+    bool have_prev = false;
+    const int nu = (int)((pitch + 1) & 3);              // the row shift goes down by nu (mod 4) per row up
+#ifdef SWB_X_BTDEBUG
+    long long dbg_walk = 0, dbg_total0 = clock64(); int dbg_bands = 0, dbg_miss = 0;
+#endif
+    if (fetcher) bt_fetch_band(bandbuf(cur), P, pitch, limit, bi, bc);
+    __syncthreads();
+    int k0 = kBtCols / 2;                               // band column of the current cell (bottom row)
+    while (true) {
+        // the band that continues this one's diagonal
+        const long long ni = bi - kBtRows, nc = bc - kBtRows;
+#ifdef SWB_X_BTSERIAL
+        if (walker) {
+#else
+        if (fetcher) {
+            if (have_prev) bt_writeback(bandbuf(cur ^ 1), listbuf(cur ^ 1), s_count[cur ^ 1], P, pitch, pbi, pbc);
+            bt_fetch_band(bandbuf(cur ^ 1), P, pitch, limit, ni, nc);
+        } else if (walker) {
+#endif
+#ifdef SWB_X_BTDEBUG
+            const long long w0 = clock64(); ++dbg_bands;
+#endif
+            const int* band = bandbuf(cur);          // (not volatile: ptxas puts a YIELD into loops with volatile loads, ~150 clk per iteration)
+            int* list = listbuf(cur);
+            long long r;
+            int sh = (int)(bt_row_start(bi, bc, pitch, kBtRows - 1, r) & 3);     // shift of the current row
+            int a = (kBtRows - 1) * kBtRS + sh + k0, cnt = 0;
+            int pv = band[a];
+            // step sizes in the staged band, packed by P code: DIAGONAL (:410) = one band row up,
+            // UP (:412) = one row up and one column right, LEFT (:414) = one column left; a row up
+            // also changes the shift from sh to (sh - nu) & 3
+            auto table = [&](int shift) {
+                const int d = ((shift - nu) & 3) - shift;
+                return (unsigned)((kBtRS - d) << 24 | 1 << 16 | (kBtRS - 1 - d) << 8);
+            };
+            unsigned tab = table(sh);
+            while (true) {
+                // speculative: address and load of the successor are issued before pv is checked, so the
+                // branch resolves in the shadow of the load (for NONE / marker / negative values the step is 0)
+                const int a2 = a - (int)__byte_perm(tab, 0u, (unsigned)pv);
+                const int pv2 = band[a2];
+                if ((unsigned)(pv - 1) >= 3u) break;
+                list[cnt++] = a;
+                sh = (pv & 1) ? ((sh - nu) & 3) : sh;                     // off the load chain
+                tab = table(sh);
+                a = a2; pv = pv2;
+            }
+            s_count[cur] = cnt;
+            s_len += cnt;
+            s_done = (pv != kBtMark);                             // NONE (or an already negated cell) ends the path (:419)
+            s_a = a;
+#ifdef SWB_X_BTDEBUG
+            dbg_walk += clock64() - w0;
+#endif
+        }
+        __syncthreads();
+#ifdef SWB_X_BTSERIAL
+        if (fetcher) {
+            if (have_prev) bt_writeback(bandbuf(cur ^ 1), listbuf(cur ^ 1), s_count[cur ^ 1], P, pitch, pbi, pbc);
+            bt_fetch_band(bandbuf(cur ^ 1), P, pitch, limit, ni, nc);
+        }
+        __syncthreads();
+#endif
+        pbi = bi; pbc = bc; have_prev = true;
+        if (s_done) break;
+        {
+            const int a = s_a;
+            const int rr = (a + kBtRS) / kBtRS - 1;               // -1 = the marker row above the band
+            long long r;
+            const long long s = bt_row_start(bi, bc, pitch, rr, r);
+            const long long g = s + (a - rr * kBtRS - (int)(s & 3));
+            i = r; j = g - r * pitch;
+        }
+        // usable prefetch: the walk left through the top and enters the next band well inside it
+        const long long kn = j - (nc - kBtCols / 2);              // its column in the next band's bottom row
+        if (i == ni && kn >= 24 && kn <= kBtCols - 24) {
+            cur ^= 1; bi = ni; bc = nc;
+            k0 = (int)kn;
+            __syncthreads();                                       // s_* read by everyone before the walker rewrites them
+        } else {
+#ifdef SWB_X_BTDEBUG
+            ++dbg_miss;
+#endif
+            // the prefetched band is useless: write back the finished one now and fetch a band centred here
+            __syncthreads();
+            if (fetcher) {
+                bt_writeback(bandbuf(cur), listbuf(cur), s_count[cur], P, pitch, pbi, pbc);
+                bi = i; bc = j;
+                bt_fetch_band(bandbuf(cur), P, pitch, limit, bi, bc);
+            }
+            have_prev = false;
+            bi = i; bc = j;
+            k0 = kBtCols / 2;
+            __syncthreads();
+        }
+    }
+    // the last band's path
+    if (fetcher) bt_writeback(bandbuf(cur), listbuf(cur), s_count[cur], P, pitch, pbi, pbc);
+    if (threadIdx.x == 0 && d_pathLen) *d_pathLen = s_len;
+#ifdef SWB_X_BTDEBUG
+    if (threadIdx.x == 0) printf("backtrack: len %lld bands %d misses %d walk clk %lld total clk %lld\n", s_len, dbg_bands, dbg_miss, dbg_walk, clock64() - dbg_total0);
+#endif
 }
 
 }  // namespace swb

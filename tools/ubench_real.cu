@@ -33,6 +33,25 @@ __global__ void k(const unsigned* aw_, int ngroups, long long* out_clk, int* sin
                 ++r;
             }
             if (mx == 0x7fffffff) *sink = mx;
+        } else if (NOISE == 3) {                 // ALU only
+            int x = w, y = lane;
+            while (!stop) { for (int i = 0; i < 64; ++i) { x = x * 3 + y; y = (y ^ x) + 7; } }
+            if (x == 0x7fffffff) *sink = x + y;
+        } else if (NOISE == 4) {                 // shared-memory loads only (LDS.32, conflict-free)
+            const int* st = reinterpret_cast<const int*>(smem4);
+            int r = 0, mx = 0;
+            while (!stop) { for (int l = 0; l < 32; ++l) mx = max(mx, st[l * kRowInts + ((32 * r + lane) & (kRowInts - 1))]); ++r; }
+            if (mx == 0x7fffffff) *sink = mx;
+        } else if (NOISE == 5) {                 // global stores only
+            int r = 0;
+            while (!stop) {
+                for (int l = 0; l < 32; ++l) { int* hp = gbuf + ((size_t)w * 64 + l) * 4096 + ((32 * r + lane) & 4095); __stcs(hp, r); __stcs(hp + 2048 * 4096, l); }
+                ++r;
+            }
+        } else if (NOISE == 6) {                 // shuffles only
+            int x = lane;
+            while (!stop) { for (int i = 0; i < 64; ++i) x = __shfl_up_sync(0xffffffffu, x, 1) + 1; }
+            if (x == 0x7fffffff) *sink = x;
         }
         return;
     }
@@ -115,5 +134,9 @@ int main()
     run<true, true, 0>(aw, ngroups, d_clk, d_sink, "in (valid), out ring", 1, gbuf);
     for (int w : {2, 3, 5, 9, 13}) run<true, true, 1>(aw, ngroups, d_clk, d_sink, "in+out, pollers", w, gbuf);
     for (int w : {2, 3, 4, 5, 7}) run<true, true, 2>(aw, ngroups, d_clk, d_sink, "in+out, writer-like", w, gbuf);
+    for (int w : {2, 4}) run<true, true, 3>(aw, ngroups, d_clk, d_sink, "in+out, ALU noise", w, gbuf);
+    for (int w : {2, 4}) run<true, true, 4>(aw, ngroups, d_clk, d_sink, "in+out, LDS noise", w, gbuf);
+    for (int w : {2, 4}) run<true, true, 5>(aw, ngroups, d_clk, d_sink, "in+out, STG noise", w, gbuf);
+    for (int w : {2, 4}) run<true, true, 6>(aw, ngroups, d_clk, d_sink, "in+out, SHFL noise", w, gbuf);
     return 0;
 }
