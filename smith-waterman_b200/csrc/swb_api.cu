@@ -72,6 +72,22 @@ struct Workspace {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// The workspace comes from the stream-ordered pool on every call: keep freed blocks in the pool
+// (the default release threshold of 0 hands them back to the driver at every synchronisation,
+// which costs milliseconds per call for the ~100 MB of band-boundary rows).
+void keep_pool_warm(int device)
+{
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    done[device] = true;
+}
+
 size_t fill_smem_bytes(int wpc)
 {
     return (size_t)wpc * (swb::kStripRows * swb::kRowInts * sizeof(int) + swb::kRing * sizeof(int4) +
@@ -184,6 +200,7 @@ int swb_fill_async(const char* a, int64_t m, const char* b, int64_t n,
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    keep_pool_warm(device);
 
     const int wpc = pick_wpc(n, tuning);
     const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
