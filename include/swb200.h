@@ -129,6 +129,23 @@ int swb_score_only(const char* a, int64_t m, const char* b, int64_t n,
                    const swb_scoring* scoring, int32_t* maxScore, int64_t* maxPos,
                    int device, void* stream);
 
+/* Asynchronous / batched score-only form: npairs equally shaped pairs (a = npairs*m bytes,
+ * b = npairs*n bytes, pair k at offset k*m / k*n), d_maxPos and d_maxScore are DEVICE arrays
+ * of npairs entries (either may be NULL).  maxPos uses pitch m+1. */
+int swb_score_only_async(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs,
+                         const swb_scoring* scoring, int64_t* d_maxPos, int32_t* d_maxScore,
+                         int device, void* stream, const swb_tuning* tuning);
+
+/* Batch of npairs independent, equally shaped pairs in ONE launch (BASELINE config "batch of
+ * 65536 independent 256x256 pairs"; the reference runs one pair per process).  Sequences are
+ * packed: a = npairs*m bytes, b = npairs*n bytes.  Pair k's matrices start at dH/dP +
+ * k*pair_stride int32 (pair_stride >= (n+1)*pitch, a multiple of 4 keeps every pair 16-byte
+ * aligned); each has the single-pair layout of swb_fill_async.  d_maxPos / d_maxScore: DEVICE
+ * arrays of npairs entries (maxPos relative to the pair's own matrix) or NULL. */
+int swb_fill_batch_async(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs,
+                         const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch, int64_t pair_stride,
+                         int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream, const swb_tuning* tuning);
+
 /* The reference's generate() (omp_smithW.c:489-519): srand(seed) then m+1 draws
  * for a and n+1 draws for b with this libc's rand(), 0->A 2->C 3->G else T.
  * Host-side helper so that callers get the reference's sequences for a seed. */

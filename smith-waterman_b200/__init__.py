@@ -17,7 +17,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-__all__ = ["lib", "SwbError", "Scoring", "DEFAULT_SCORING", "generate", "fill", "fill_async", "backtrack", "backtrack_async",
+__all__ = ["lib", "SwbError", "Scoring", "DEFAULT_SCORING", "generate", "fill", "fill_async", "fill_batch_async", "score_only_async", "backtrack", "backtrack_async",
            "smithWaterman", "align_host", "AlignContext", "score_only", "KernelTimer", "host_alloc", "host_free",
            "device_count", "LIB_PATH", "NONE", "UP", "LEFT", "DIAGONAL", "PATH"]
 
@@ -67,6 +67,9 @@ def _load() -> C.CDLL:
     L.swb_ctx_dP.argtypes = [vp]; L.swb_ctx_dP.restype = vp
     L.swb_ctx_destroy.argtypes = [vp]; L.swb_ctx_destroy.restype = None
     L.swb_score_only.argtypes = [vp, i64, vp, i64, C.POINTER(Scoring), C.POINTER(i32), C.POINTER(i64), C.c_int, vp]
+    L.swb_score_only_async.argtypes = [vp, i64, vp, i64, i64, C.POINTER(Scoring), vp, vp, C.c_int, vp, C.POINTER(Tuning)]
+    L.swb_fill_batch_async.argtypes = [vp, i64, vp, i64, i64, C.POINTER(Scoring), vp, vp, i64, i64, vp, vp, C.c_int, vp,
+                                       C.POINTER(Tuning)]
     L.swb_generate.argtypes = [C.c_uint, i64, i64, vp, vp]; L.swb_generate.restype = None
     L.swb_timer_create.argtypes = [C.POINTER(vp), C.c_int]; L.swb_timer_create.restype = C.c_int
     L.swb_timer_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]; L.swb_timer_elapsed_ms.restype = C.c_int
@@ -74,7 +77,7 @@ def _load() -> C.CDLL:
     L.swb_host_alloc.argtypes = [C.c_size_t]; L.swb_host_alloc.restype = vp
     L.swb_host_free.argtypes = [vp]; L.swb_host_free.restype = None
     for name in ("swb_fill_async", "swb_fill", "swb_backtrack_async", "swb_backtrack", "swb_align_host",
-                 "swb_ctx_create", "swb_ctx_align", "swb_score_only"):
+                 "swb_ctx_create", "swb_ctx_align", "swb_score_only", "swb_score_only_async", "swb_fill_batch_async"):
         getattr(L, name).restype = C.c_int
     return L
 
@@ -136,6 +139,28 @@ def fill_async(a, m: int, b, n: int, dH, dP, pitch: int | None = None, d_maxPos=
                  trace=_ptr(trace) if trace is not None else None)
     _check(lib.swb_fill_async(_ptr(a), m, _ptr(b), n, C.byref(sc), _ptr(dH), _ptr(dP), pitch or m + 1,
                               _ptr(d_maxPos), _ptr(d_maxScore), device, _stream_ptr(stream), C.byref(tun)))
+
+
+def fill_batch_async(a, m: int, b, n: int, npairs: int, dH, dP, pitch: int | None = None, pair_stride: int | None = None,
+                     d_maxPos=None, d_maxScore=None, scoring=None, device: int = 0, stream=None, warps_per_band: int = 0,
+                     timer=None) -> None:
+    """Enqueue the fill of npairs equally shaped pairs in one launch.  a: npairs*m bytes, b: npairs*n bytes
+    (host or device); pair k's H/P start at dH/dP + k*pair_stride int32."""
+    sc = _scoring(scoring)
+    pitch = pitch or m + 1
+    pair_stride = pair_stride or (n + 1) * pitch
+    tun = Tuning(warps_per_band=warps_per_band, timer=timer._h if timer is not None else None)
+    _check(lib.swb_fill_batch_async(_ptr(a), m, _ptr(b), n, npairs, C.byref(sc), _ptr(dH), _ptr(dP), pitch, pair_stride,
+                                    _ptr(d_maxPos), _ptr(d_maxScore), device, _stream_ptr(stream), C.byref(tun)))
+
+
+def score_only_async(a, m: int, b, n: int, npairs: int = 1, d_maxPos=None, d_maxScore=None, scoring=None,
+                     device: int = 0, stream=None, warps_per_band: int = 0, timer=None) -> None:
+    """Enqueue the score-only kernel (no H/P stores) for npairs equally shaped pairs."""
+    sc = _scoring(scoring)
+    tun = Tuning(warps_per_band=warps_per_band, timer=timer._h if timer is not None else None)
+    _check(lib.swb_score_only_async(_ptr(a), m, _ptr(b), n, npairs, C.byref(sc), _ptr(d_maxPos), _ptr(d_maxScore), device,
+                                    _stream_ptr(stream), C.byref(tun)))
 
 
 def fill(a, m: int, b, n: int, dH, dP, pitch: int | None = None, scoring=None, device: int = 0, stream=None) -> int:

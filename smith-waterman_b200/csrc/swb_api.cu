@@ -68,6 +68,7 @@ struct Workspace {
     int* ticket = nullptr; int* gmax = nullptr; unsigned long long* key = nullptr;
     int* strip_max = nullptr;
     int4* boundary = nullptr; long long bstride = 0;
+    unsigned long long* row_best = nullptr;
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -88,24 +89,151 @@ void keep_pool_warm(int device)
     done[device] = true;
 }
 
-size_t fill_smem_bytes(int wpc)
-{
-    return (size_t)wpc * (swb::kStripRows * swb::kRowInts * sizeof(int) + swb::kRing * sizeof(int4) +
-                          swb::kWriters * 32 * sizeof(int4));
-}
-
-int pick_wpc(int64_t n, const swb_tuning* tuning)
+int pick_wpc(int64_t n, int kt, bool store, const swb_tuning* tuning)
 {
     int wpc = 2;
     if (const char* e = std::getenv("SWB_WPC")) wpc = std::atoi(e);
     if (tuning && tuning->warps_per_band > 0) wpc = tuning->warps_per_band;
     wpc = std::max(1, std::min(wpc, swb::kMaxWpc));
-    while (wpc > 1 && fill_smem_bytes(wpc) + 2048 > 227 * 1024) --wpc;     // 227 KB of shared memory per CTA on sm_100
+    while (wpc > 1 && swb::fill_smem_bytes(wpc, kt, store) + 2048 > 227 * 1024) --wpc;     // 227 KB of shared memory per CTA on sm_100
     const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
     if (strips < wpc) wpc = (int)strips;
     return wpc;
 }
 
+template <int KT, bool STORE>
+cudaError_t launch_fill(const swb::FillParams& p, long long nblocks, int wpc, cudaStream_t st)
+{
+    const size_t smem = swb::fill_smem_bytes(wpc, KT, STORE);
+    cudaError_t e = cudaFuncSetAttribute(swb::fill_kernel<KT, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    swb::fill_kernel<KT, STORE><<<(unsigned)nblocks, swb::fill_block_threads(wpc, STORE), smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// The one implementation behind swb_fill_async, swb_fill_batch_async and swb_score_only_async.
+//   npairs equally shaped pairs: a = npairs*m bytes, b = npairs*n bytes, pair k's matrices at
+//   dH/dP + k*pair_stride; d_maxPos / d_maxScore hold npairs entries.  store == false: score only.
+int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs, const swb_scoring* scoring,
+              int32_t* dH, int32_t* dP, int64_t pitch, int64_t pair_stride, int64_t* d_maxPos, int32_t* d_maxScore,
+              int device, void* stream, const swb_tuning* tuning, bool store)
+{
+    if (!a || !b || m <= 0 || n <= 0 || npairs <= 0) return SWB_ERR_ARG;
+    if (store && (!dH || !dP || pitch < m + 1)) return SWB_ERR_ARG;
+    if (store && npairs > 1 && pair_stride < (n + 1) * pitch) return SWB_ERR_ARG;
+    if (m >= (1LL << 30) || n >= (1LL << 30)) return SWB_ERR_RANGE;
+    if (store && ((reinterpret_cast<uintptr_t>(dH) & 15) || (reinterpret_cast<uintptr_t>(dP) & 15))) return SWB_ERR_ALIGN;
+    const swb_scoring sc = scoring ? *scoring : kDefaultScoring;
+    if (int rc = check_scoring(sc, m, n)) return rc;
+    if (!store) pitch = m + 1;
+
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    keep_pool_warm(device);
+
+    // single large pairs: deep staging ring, one CTA per SM; batches of small pairs: shallow ring, more CTAs per SM
+    const int kt = (npairs > 1) ? 32 : 64;
+    const int wpc = pick_wpc(n, kt, store, tuning);
+    const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
+    const int nbands = (int)((strips + wpc - 1) / wpc);
+    if ((long long)nbands * npairs >= (1LL << 31)) return SWB_ERR_RANGE;
+    const int jmax = (int)(m >> 2);                                   // last block with a valid column
+    const int ngroups = (jmax + 1 + 31 + swb::kGroup - 1) / swb::kGroup;
+
+    // ---- workspace (stream ordered)
+    Workspace ws;
+    ws.a4_words = swb::kAPad + (long long)ngroups * swb::kGroup + 16;
+    ws.bstride = (long long)ngroups * swb::kGroup;
+    const bool a_on_dev = is_device_ptr(a), b_on_dev = is_device_ptr(b);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_a4 = carve((size_t)npairs * ws.a4_words * sizeof(unsigned));
+    const size_t o_a = carve(a_on_dev ? 0 : (size_t)(m * npairs));
+    const size_t o_b = carve(b_on_dev ? 0 : (size_t)(n * npairs));
+    const size_t o_small = carve(256);
+    const size_t o_gmax = carve((size_t)npairs * sizeof(int));
+    const size_t o_key = carve((size_t)npairs * sizeof(unsigned long long));
+    const size_t o_smax = carve((size_t)(strips * npairs) * sizeof(int));
+    const size_t boundary_bytes = (size_t)npairs * (size_t)std::max(nbands - 1, 0) * (size_t)ws.bstride * sizeof(int4);
+    const size_t o_bnd = carve(boundary_bytes);
+    const size_t o_rb = carve(store ? 0 : (size_t)npairs * (size_t)(n + 1) * sizeof(unsigned long long));
+    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws.base), off, st));
+    ws.a4 = reinterpret_cast<unsigned*>(ws.base + o_a4);
+    ws.a_dev = ws.base + o_a; ws.b_dev = ws.base + o_b;
+    ws.ticket = reinterpret_cast<int*>(ws.base + o_small);
+    ws.gmax = reinterpret_cast<int*>(ws.base + o_gmax);
+    ws.key = reinterpret_cast<unsigned long long*>(ws.base + o_key);
+    ws.strip_max = reinterpret_cast<int*>(ws.base + o_smax);
+    ws.boundary = reinterpret_cast<int4*>(ws.base + o_bnd);
+    ws.row_best = reinterpret_cast<unsigned long long*>(ws.base + o_rb);
+
+    int rc = SWB_OK;
+    auto run = [&]() -> int {
+        const unsigned char* a_d = reinterpret_cast<const unsigned char*>(a);
+        const unsigned char* b_d = reinterpret_cast<const unsigned char*>(b);
+        if (!a_on_dev) { SWB_CUDA(cudaMemcpyAsync(ws.a_dev, a, (size_t)(m * npairs), cudaMemcpyHostToDevice, st)); a_d = ws.a_dev; }
+        if (!b_on_dev) { SWB_CUDA(cudaMemcpyAsync(ws.b_dev, b, (size_t)(n * npairs), cudaMemcpyHostToDevice, st)); b_d = ws.b_dev; }
+        if (store) {
+            // row 0 of H and P (the reference gets it from calloc, omp_smithW.c:113-118)
+            if (npairs == 1) {
+                SWB_CUDA(cudaMemsetAsync(dH, 0, (size_t)(m + 1) * sizeof(int32_t), st));
+                SWB_CUDA(cudaMemsetAsync(dP, 0, (size_t)(m + 1) * sizeof(int32_t), st));
+            } else {
+                SWB_CUDA(cudaMemset2DAsync(dH, (size_t)pair_stride * sizeof(int32_t), 0, (size_t)(m + 1) * sizeof(int32_t), (size_t)npairs, st));
+                SWB_CUDA(cudaMemset2DAsync(dP, (size_t)pair_stride * sizeof(int32_t), 0, (size_t)(m + 1) * sizeof(int32_t), (size_t)npairs, st));
+            }
+        }
+        // band-boundary rows carry their validity tag in the data: clear the tags
+        if (boundary_bytes) SWB_CUDA(cudaMemsetAsync(ws.boundary, 0, boundary_bytes, st));
+        const int prep_blocks = (int)std::min<int64_t>((ws.a4_words * npairs + 255) / 256, 1184);
+        swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, npairs, ws.a4, ws.a4_words, ws.ticket, ws.gmax, ws.key,
+                                                      ws.strip_max, (long long)(strips * npairs));
+        SWB_CUDA(cudaGetLastError());
+
+        swb::FillParams p{};
+        p.a4 = ws.a4; p.b = b_d;
+        p.H = dH; p.P = dP; p.pitch = pitch; p.m = m; p.n = n;
+        p.s_match = 16 * sc.match + swb::kTieDiag;
+        p.s_mismatch = 16 * sc.mismatch + swb::kTieDiag;
+        p.g_up = 16 * sc.gap + swb::kTieUp;
+        p.g_left = 16 * sc.gap + swb::kTieLeft;
+        p.ngroups = ngroups; p.jmax = jmax; p.wpc = wpc;
+        p.boundary = ws.boundary; p.bstride = ws.bstride;
+        p.ticket = ws.ticket; p.strip_max = ws.strip_max; p.gmax = ws.gmax;
+        p.trace = tuning ? reinterpret_cast<unsigned long long*>(tuning->trace) : nullptr;
+        p.nbands = nbands; p.nstrips = strips; p.a4_stride = ws.a4_words; p.pair_stride = pair_stride;
+        p.row_best = ws.row_best;
+        swb_timer* timer = tuning ? tuning->timer : nullptr;
+        if (timer) SWB_CUDA(cudaEventRecord(timer->start, st));
+        const long long nblocks = (long long)nbands * npairs;
+        cudaError_t e;
+        if (!store)        e = launch_fill<64, false>(p, nblocks, wpc, st);
+        else if (kt == 64) e = launch_fill<64, true>(p, nblocks, wpc, st);
+        else               e = launch_fill<32, true>(p, nblocks, wpc, st);
+        if (e != cudaSuccess) return cuda_fail(e, "fill_kernel launch", __LINE__);
+        if (timer) SWB_CUDA(cudaEventRecord(timer->stop, st));
+
+        if (store) {
+            const int am_blocks = (npairs > 1) ? 1 : (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
+            swb::argmax_kernel<<<dim3((unsigned)am_blocks, (unsigned)npairs), 256, 0, st>>>(dH, pitch, pair_stride, m, n, ws.strip_max,
+                                                                                              ws.gmax, ws.key);
+            SWB_CUDA(cudaGetLastError());
+            swb::finalize_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(ws.key, ws.gmax, pitch, npairs,
+                                                                                   reinterpret_cast<long long*>(d_maxPos), d_maxScore);
+            SWB_CUDA(cudaGetLastError());
+        } else {
+            swb::rowbest_argmax_kernel<<<(unsigned)npairs, 256, 0, st>>>(ws.row_best, n, pitch, ws.gmax,
+                                                                        reinterpret_cast<long long*>(d_maxPos), d_maxScore);
+            SWB_CUDA(cudaGetLastError());
+        }
+        return SWB_OK;
+    };
+    rc = run();
+    cudaError_t fe = cudaFreeAsync(ws.base, st);
+    if (rc == SWB_OK && fe != cudaSuccess) rc = cuda_fail(fe, "cudaFreeAsync", __LINE__);
+    return rc;
+}
 
 }  // namespace
 
@@ -125,7 +253,7 @@ const char* swb_strerror(int status)
 }
 
 const char* swb_last_cuda_error(void) { return g_cuda_err; }
-int swb_version(void) { return 100; }
+int swb_version(void) { return 110; }
 
 int swb_device_count(void)
 {
@@ -191,92 +319,23 @@ int swb_fill_async(const char* a, int64_t m, const char* b, int64_t n,
                    int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream,
                    const swb_tuning* tuning)
 {
-    if (!a || !b || !dH || !dP || m <= 0 || n <= 0 || pitch < m + 1) return SWB_ERR_ARG;
-    if (m >= (1LL << 30) || n >= (1LL << 30)) return SWB_ERR_RANGE;
-    if ((reinterpret_cast<uintptr_t>(dH) & 15) || (reinterpret_cast<uintptr_t>(dP) & 15)) return SWB_ERR_ALIGN;
-    const swb_scoring sc = scoring ? *scoring : kDefaultScoring;
-    if (int rc = check_scoring(sc, m, n)) return rc;
+    return fill_impl(a, m, b, n, 1, scoring, dH, dP, pitch, 0, d_maxPos, d_maxScore, device, stream, tuning, true);
+}
 
-    DeviceGuard guard(device);
-    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    keep_pool_warm(device);
+int swb_fill_batch_async(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs,
+                         const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch, int64_t pair_stride,
+                         int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream, const swb_tuning* tuning)
+{
+    return fill_impl(a, m, b, n, npairs, scoring, dH, dP, pitch, pair_stride, d_maxPos, d_maxScore, device, stream,
+                     tuning, true);
+}
 
-    const int wpc = pick_wpc(n, tuning);
-    const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
-    const int nbands = (int)((strips + wpc - 1) / wpc);
-    const int jmax = (int)(m >> 2);                                   // last block with a valid column
-    const int ngroups = (jmax + 1 + 31 + swb::kGroup - 1) / swb::kGroup;
-
-    // ---- workspace (stream ordered)
-    Workspace ws;
-    ws.a4_words = swb::kAPad + (long long)ngroups * swb::kGroup + 16;
-    ws.bstride = (long long)ngroups * swb::kGroup;
-    const bool a_on_dev = is_device_ptr(a), b_on_dev = is_device_ptr(b);
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_a4 = carve((size_t)ws.a4_words * sizeof(unsigned));
-    const size_t o_a = carve(a_on_dev ? 0 : (size_t)m);
-    const size_t o_b = carve(b_on_dev ? 0 : (size_t)n);
-    const size_t o_small = carve(256);
-    const size_t o_smax = carve((size_t)strips * sizeof(int));
-    const size_t boundary_bytes = (size_t)std::max(nbands - 1, 0) * (size_t)ws.bstride * sizeof(int4);
-    const size_t o_bnd = carve(boundary_bytes);
-    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws.base), off, st));
-    ws.a4 = reinterpret_cast<unsigned*>(ws.base + o_a4);
-    ws.a_dev = ws.base + o_a; ws.b_dev = ws.base + o_b;
-    ws.ticket = reinterpret_cast<int*>(ws.base + o_small);
-    ws.gmax = ws.ticket + 1;
-    ws.key = reinterpret_cast<unsigned long long*>(ws.base + o_small + 16);
-    ws.strip_max = reinterpret_cast<int*>(ws.base + o_smax);
-    ws.boundary = reinterpret_cast<int4*>(ws.base + o_bnd);
-
-    int rc = SWB_OK;
-    auto run = [&]() -> int {
-        const unsigned char* a_d = reinterpret_cast<const unsigned char*>(a);
-        const unsigned char* b_d = reinterpret_cast<const unsigned char*>(b);
-        if (!a_on_dev) { SWB_CUDA(cudaMemcpyAsync(ws.a_dev, a, (size_t)m, cudaMemcpyHostToDevice, st)); a_d = ws.a_dev; }
-        if (!b_on_dev) { SWB_CUDA(cudaMemcpyAsync(ws.b_dev, b, (size_t)n, cudaMemcpyHostToDevice, st)); b_d = ws.b_dev; }
-        // row 0 of H and P (the reference gets it from calloc, omp_smithW.c:113-118)
-        SWB_CUDA(cudaMemsetAsync(dH, 0, (size_t)(m + 1) * sizeof(int32_t), st));
-        SWB_CUDA(cudaMemsetAsync(dP, 0, (size_t)(m + 1) * sizeof(int32_t), st));
-        // band-boundary rows carry their validity tag in the data: clear the tags
-        if (boundary_bytes) SWB_CUDA(cudaMemsetAsync(ws.boundary, 0, boundary_bytes, st));
-        const int prep_blocks = (int)std::min<int64_t>((ws.a4_words + 255) / 256, 1184);
-        swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, ws.a4, ws.a4_words, ws.ticket, ws.gmax, ws.key, ws.strip_max,
-                                                      (long long)strips);
-        SWB_CUDA(cudaGetLastError());
-
-        swb::FillParams p{};
-        p.a4 = ws.a4; p.b = b_d;
-        p.H = dH; p.P = dP; p.pitch = pitch; p.m = m; p.n = n;
-        p.s_match = 16 * sc.match + swb::kTieDiag;
-        p.s_mismatch = 16 * sc.mismatch + swb::kTieDiag;
-        p.g_up = 16 * sc.gap + swb::kTieUp;
-        p.g_left = 16 * sc.gap + swb::kTieLeft;
-        p.ngroups = ngroups; p.jmax = jmax; p.wpc = wpc;
-        p.boundary = ws.boundary; p.bstride = ws.bstride;
-        p.ticket = ws.ticket; p.strip_max = ws.strip_max; p.gmax = ws.gmax;
-        p.trace = tuning ? reinterpret_cast<unsigned long long*>(tuning->trace) : nullptr;
-        const size_t smem = fill_smem_bytes(wpc);
-        SWB_CUDA(cudaFuncSetAttribute(swb::fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        swb_timer* timer = tuning ? tuning->timer : nullptr;
-        if (timer) SWB_CUDA(cudaEventRecord(timer->start, st));
-        swb::fill_kernel<<<nbands, swb::fill_block_threads(wpc), smem, st>>>(p);
-        SWB_CUDA(cudaGetLastError());
-        if (timer) SWB_CUDA(cudaEventRecord(timer->stop, st));
-
-        const int am_blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
-        swb::argmax_kernel<<<am_blocks, 256, 0, st>>>(dH, pitch, m, n, ws.strip_max, ws.gmax, ws.key);
-        SWB_CUDA(cudaGetLastError());
-        swb::finalize_kernel<<<1, 1, 0, st>>>(ws.key, ws.gmax, pitch, reinterpret_cast<long long*>(d_maxPos), d_maxScore);
-        SWB_CUDA(cudaGetLastError());
-        return SWB_OK;
-    };
-    rc = run();
-    cudaError_t fe = cudaFreeAsync(ws.base, st);
-    if (rc == SWB_OK && fe != cudaSuccess) rc = cuda_fail(fe, "cudaFreeAsync", __LINE__);
-    return rc;
+int swb_score_only_async(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs,
+                         const swb_scoring* scoring, int64_t* d_maxPos, int32_t* d_maxScore,
+                         int device, void* stream, const swb_tuning* tuning)
+{
+    return fill_impl(a, m, b, n, npairs, scoring, nullptr, nullptr, m + 1, 0, d_maxPos, d_maxScore, device, stream,
+                     tuning, false);
 }
 
 int swb_fill(const char* a, int64_t m, const char* b, int64_t n,
@@ -419,26 +478,21 @@ int swb_score_only(const char* a, int64_t m, const char* b, int64_t n,
                    const swb_scoring* scoring, int32_t* maxScore, int64_t* maxPos,
                    int device, void* stream)
 {
-    // PROVISIONAL (round 1): runs the full fill into temporary matrices and drops them.
-    // The dedicated no-store kernel replaces this.
     if (m <= 0 || n <= 0) return SWB_ERR_ARG;
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t bytes = (size_t)(m + 1) * (size_t)(n + 1) * sizeof(int32_t);
-    int32_t *dH = nullptr, *dP = nullptr; long long* d_pos = nullptr; int32_t* d_sc = nullptr;
-    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dH), bytes, st));
-    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dP), bytes, st));
+    long long* d_pos = nullptr;
     SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_pos), 16, st));
-    d_sc = reinterpret_cast<int32_t*>(d_pos + 1);
-    int rc = swb_fill_async(a, m, b, n, scoring, dH, dP, m + 1, reinterpret_cast<int64_t*>(d_pos), d_sc, device, stream, nullptr);
+    int32_t* d_sc = reinterpret_cast<int32_t*>(d_pos + 1);
+    int rc = swb_score_only_async(a, m, b, n, 1, scoring, reinterpret_cast<int64_t*>(d_pos), d_sc, device, stream, nullptr);
     long long host[2] = {0, 0};
     if (rc == SWB_OK) {
         cudaError_t e = cudaMemcpyAsync(host, d_pos, 16, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = cuda_fail(e, "score readback", __LINE__);
     }
-    cudaFreeAsync(dH, st); cudaFreeAsync(dP, st); cudaFreeAsync(d_pos, st);
+    cudaFreeAsync(d_pos, st);
     if (rc == SWB_OK) {
         if (maxPos) *maxPos = host[0];
         if (maxScore) *maxScore = (int32_t)(host[1] & 0xffffffff);

@@ -55,11 +55,8 @@ namespace swb {
 constexpr int kR        = SWB_ROWS_PER_LANE;   // adjacent rows per lane
 constexpr int kStripRows = 32 * kR;    // rows per strip (compute warp)
 constexpr int kWriters  = kR;          // writer warps per strip, 32 rows each
-#ifndef SWB_KT
-#define SWB_KT 64
-#endif
-constexpr int kT        = SWB_KT;      // staging ring depth in steps (16-byte slots per row)
-constexpr int kRowInts  = 4 * kT;      // ints per row of the staging ring
+// KT (template parameter of the fill kernel) = staging ring depth in steps (16-byte slots per
+// row): 64 for single large pairs, 32 for batches of small pairs (more CTAs per SM)
 constexpr int kRing     = 64;          // hand-off ring capacity in blocks (power of two)
 constexpr int kGroup    = 8;           // steps per synchronisation group
 constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
@@ -67,8 +64,8 @@ constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: com
                                        // writers + loader on the others
 constexpr int kDrainRounds = 2;        // writer rounds after the last compute group
 // writer round r reads steps [8r-8, 8r+7]; compute group g overwrites the slots of group
-// g - kT/8, which rounds <= g - kT/8 + 1 read: g may start once that many rounds are done
-constexpr int kStageSlack = kT / kGroup - 2;
+// g - KT/8, which rounds <= g - KT/8 + 1 read: g may start once that many rounds are done
+__host__ __device__ constexpr int stage_slack(int KT) { return KT / kGroup - 2; }
 
 // tie codes: larger wins on equal score => NONE > DIAGONAL > UP > LEFT, and code&3 is
 // the reference's P value (omp_smithW.c:33-36)
@@ -92,6 +89,13 @@ struct FillParams {
     int*            strip_max;             // [nstrips] max H of each strip (atomicMax by its writers)
     int*            gmax;                  // global max H
     unsigned long long* trace;             // optional [nstrips][8] globaltimer stamps (developer tool) or nullptr
+    // batches of equally shaped pairs: pair k uses a4 + k*a4_stride, b + k*n, H/P + k*pair_stride,
+    // boundary + k*(nbands-1)*bstride, strip_max + k*nstrips, gmax + k, row_best + k*(n+1)
+    int             nbands;                // bands per pair
+    long long       nstrips;               // strips per pair
+    long long       a4_stride, pair_stride;
+    // score-only mode (no H/P stores): per-row best cell, packed (score << 32) | (0xffffffff - column)
+    unsigned long long* row_best;
 };
 
 __device__ __forceinline__ void trace_stamp(const FillParams& p, long long strip, int slot, int lane)
@@ -179,32 +183,37 @@ __device__ __forceinline__ int opaque(int x) { return __shfl_sync(0xffffffffu, x
 // 4j..4j+3; column c reads a[c-1], omp_smithW.c:395), zero outside the sequence --
 // and arms the workspace words.
 // ---------------------------------------------------------------------------------
-__global__ void prep_kernel(const unsigned char* __restrict__ a, long long m,
+__global__ void prep_kernel(const unsigned char* __restrict__ a, long long m, long long npairs,
                             unsigned* __restrict__ a4, long long nwords,
                             int* ticket, int* gmax, unsigned long long* key,
-                            int* strip_max, long long nstrips)
+                            int* strip_max, long long nstrips_total)
 {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
-    for (long long w = tid; w < nwords; w += nth) {
+    for (long long x = tid; x < nwords * npairs; x += nth) {
+        const long long pair = x / nwords, w = x % nwords;
+        const unsigned char* ap = a + pair * m;
         const long long base = 4 * (w - kAPad) - 1;
         unsigned word = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const long long idx = base + e;
-            const unsigned c = (idx >= 0 && idx < m) ? (unsigned)a[idx] : 0u;
+            const unsigned c = (idx >= 0 && idx < m) ? (unsigned)ap[idx] : 0u;
             word |= c << (8 * e);
         }
-        a4[w] = word;
+        a4[x] = word;
     }
-    for (long long k = tid; k < nstrips; k += nth) strip_max[k] = 0;
-    if (tid == 0) { *ticket = 0; *gmax = 0; *key = ~0ull; }
+    for (long long k = tid; k < nstrips_total; k += nth) strip_max[k] = 0;
+    for (long long k = tid; k < npairs; k += nth) { gmax[k] = 0; key[k] = ~0ull; }
+    if (tid == 0) *ticket = 0;
 }
 
 // ---------------------------------------------------------------------------------
 // compute warp
 // ---------------------------------------------------------------------------------
+template <int KT, bool STORE>
 struct Strip {
+    static constexpr int kRowInts = 4 * KT;
     int lane;
     unsigned b4[kR];              // my rows' characters, replicated in the four bytes
     int sm, sx, gu, gl;
@@ -221,6 +230,8 @@ struct Strip {
     int   has_in;                 // a strip above exists
     int   out_ring, out_glob;     // THIS LANE hands blocks on (lane 31 only): to the ring / to global
     int   jmax;
+    int   mcols;                  // m
+    int   rmax[kR], rcol[kR];     // score-only: best clean 16*H of each of my rows and its first column
 
     __device__ __forceinline__ void scores(const unsigned aword)
     {
@@ -285,14 +296,33 @@ struct Strip {
             const int h3 = k3 & ~15;
             if (q == kR - 1) n3 = __shfl_up_sync(0xffffffffu, h3, 1);
             hl[q] = h3;
-            // stage the packed block of this row for the writers
-            if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
-            if (q == 1) sts_int4<kRowInts * 4>(sa, k0, k1, k2, k3);
-            if (q == 2) sts_int4<2 * kRowInts * 4>(sa, k0, k1, k2, k3);
-            if (q == 3) sts_int4<3 * kRowInts * 4>(sa, k0, k1, k2, k3);
+            if (STORE) {
+                // stage the packed block of this row for the writers
+                if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
+                if (q == 1) sts_int4<kRowInts * 4>(sa, k0, k1, k2, k3);
+                if (q == 2) sts_int4<2 * kRowInts * 4>(sa, k0, k1, k2, k3);
+                if (q == 3) sts_int4<3 * kRowInts * 4>(sa, k0, k1, k2, k3);
+            } else {
+                // score only: remember the first column of this row that reaches its maximum
+                // (strict '>' keeps the earliest column, i.e. the earliest anti-diagonal of the row);
+                // branch-free -- the compute warp must not diverge
+                int v0 = h0, v1 = h1, v2 = h2, v3 = h3;
+                if (EDGE) {
+                    const int c = 4 * j;
+                    v0 = (c >= 1 && c <= mcols) ? h0 : -1;
+                    v1 = (c + 1 >= 1 && c + 1 <= mcols) ? h1 : -1;
+                    v2 = (c + 2 >= 1 && c + 2 <= mcols) ? h2 : -1;
+                    v3 = (c + 3 >= 1 && c + 3 <= mcols) ? h3 : -1;
+                }
+                const int bm = max(max(v0, v1), max(v2, v3));
+                const int e = (v0 == bm) ? 0 : (v1 == bm) ? 1 : (v2 == bm) ? 2 : 3;
+                const bool upd = bm > rmax[q];
+                rcol[q] = upd ? 4 * j + e : rcol[q];
+                rmax[q] = upd ? bm : rmax[q];
+            }
             u0 = h0; u1 = h1; u2 = h2; u3 = h3;          // the row above the next row
         }
-        sa = ((sa + 16u) & (unsigned)(kT * 16 - 1)) | sa_base;
+        if (STORE) sa = ((sa + 16u) & (unsigned)(KT * 16 - 1)) | sa_base;
 
         // ---------------- hand my last row to the next strip (lane 31 only) ----------------
         {
@@ -330,7 +360,8 @@ struct Strip {
 // the staged data and its flag relies on the in-order shared-memory pipeline of one warp
 // (data STS, __syncwarp, flag STS; flag LDS, data LDS): a MEMBAR here waits for the writer's
 // outstanding GLOBAL stores as well and cost ~2500 clk per round.
-__device__ __forceinline__ void compute_strip(const FillParams& p, Strip& S, const unsigned* aw,
+template <int KT, bool STORE>
+__device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STORE>& S, const unsigned* aw,
                                               const unsigned staged, const unsigned drained,
                                               const unsigned consumed_in, const unsigned consumed_out,
                                               const bool ring_consumer, const long long strip)
@@ -364,12 +395,10 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip& S, con
         const long long gc0 = clock64();
 #endif
         // ---- staging ring space: the writers must have drained the slots this group overwrites
-#ifndef SWB_X_NOWRITER
-        if (g > kStageSlack) {
+        if (STORE && g > stage_slack(KT)) {
 #pragma unroll
-            for (int k = 0; k < kWriters; ++k) spin_until_ge(drained + 4u * k, g - kStageSlack);
+            for (int k = 0; k < kWriters; ++k) spin_until_ge(drained + 4u * k, g - stage_slack(KT));
         }
-#endif
         // ---- hand-off ring space (blocks up to t0+7-31 are written in this group)
         if (ring_consumer && t0 - 80 > 0) spin_until_ge(consumed_out, t0 - 80);
         sts_volatile_int_if(consumed_in, t0, S.has_in & (lane == 0 ? 1 : 0));
@@ -409,7 +438,7 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip& S, con
         for (int i = 0; i < kGroup; ++i) cur[i] = nxt[i];
         // ---- publish the staged group to the writers
         __syncwarp();
-        sts_volatile_int_if(staged, g + 1, lane == 0 ? 1 : 0);
+        if (STORE) sts_volatile_int_if(staged, g + 1, lane == 0 ? 1 : 0);
 #ifdef SWB_X_GROUPTRACE
         { const long long gc3 = clock64();
           if (g >= 8) { dbg_pre += gc1 - gc0; dbg_steps += gc2 - gc1; dbg_post += gc3 - gc2; ++dbg_n; }
@@ -430,8 +459,9 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip& S, con
 // writer warp: drains 32 rows of the staging ring of one strip into H and P
 //   sub = which 32 rows of the strip (0 .. kWriters-1)
 // ---------------------------------------------------------------------------------
+template <int KT>
 __device__ __forceinline__ void writer_strip(const FillParams& p, const long long r0, const int sub, const int lane,
-                                             const int* stage /* this strip: [32*kR][kRowInts] */,
+                                             const int* stage /* this strip: [32*kR][4*KT] */,
                                              int4* rowtab,
                                              volatile int* staged, volatile int* drained, const long long strip)
 {
@@ -439,6 +469,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
     // per-row constants: round r flushes, for this row, the 32 columns 32r-E .. 32r-E+31 whose
     // first element sits on a 128-byte line of H (and P); E is the smallest such offset for
     // which lane cl has finished those columns by the end of compute group r
+    constexpr int kRowInts = 4 * KT;
     const int rho = 32 * sub + lane;
     const int cl  = rho / kR;
     const long long row = r0 + rho;
@@ -454,9 +485,6 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
     const int Emin = __reduce_min_sync(0xffffffffu, E);
     __syncwarp();
     const int* mystage = stage + (size_t)32 * sub * kRowInts;
-#ifdef SWB_X_NOWRITER
-    return;
-#endif
 
     int mx = 0;
     const int rounds = p.ngroups + kDrainRounds;
@@ -564,19 +592,26 @@ __device__ __forceinline__ void loader_band(const int4* src, const int nblocks, 
 }
 
 // threads per block for wpc strips per band: rows of 4 warps; the 4-wpc serving schedulers
-// hold wpc*kWriters writers + 1 loader
-__host__ __device__ constexpr int fill_block_threads(int wpc)
+// hold wpc*kWriters writers (none in score-only mode) + 1 loader
+__host__ __device__ constexpr int fill_block_threads(int wpc, bool store)
 {
-    return 32 * 4 * ((wpc * kWriters + 1 + (4 - wpc) - 1) / (4 - wpc));
+    return 32 * 4 * (((store ? wpc * kWriters : 0) + 1 + (4 - wpc) - 1) / (4 - wpc));
+}
+__host__ __device__ constexpr size_t fill_smem_bytes(int wpc, int KT, bool store)
+{
+    return (size_t)wpc * ((store ? (size_t)kStripRows * 4 * KT * sizeof(int) + kWriters * 32 * sizeof(int4) : 0) +
+                          kRing * sizeof(int4));
 }
 
 // ---------------------------------------------------------------------------------
-// The fill kernel.  grid = number of bands, block = fill_block_threads(wpc) threads (roles by
-// warp id, see below): wpc compute warps, wpc*kWriters writers, one loader of the band boundary.
-// dynamic smem = wpc * (kStripRows*kRowInts*4 + kRing*16 + kWriters*32*16) bytes.
+// The fill kernel.  grid = number of bands (x pairs), block = fill_block_threads(wpc) threads
+// (roles by warp id, see below): wpc compute warps, wpc*kWriters writers, one loader of the
+// band boundary.  dynamic smem = fill_smem_bytes(wpc, KT, STORE).
+// STORE = false is the score-only variant: no staging, no writers, per-row best cells instead.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(fill_block_threads(kMaxWpc))
-fill_kernel(const FillParams p)
+template <int KT, bool STORE>
+__global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true))
+fill_kernel(const FillParams p_in)
 {
     extern __shared__ __align__(1024) int4 smem4[];
     __shared__ int s_band;
@@ -584,14 +619,14 @@ fill_kernel(const FillParams p)
 
     const int lane = threadIdx.x & 31;
     const int wid  = threadIdx.x >> 5;
-    const int wpc  = p.wpc;
+    const int wpc  = p_in.wpc;
     // Warp roles by scheduler (a warp runs on SM sub-partition wid % 4).  A compute warp must
     // not share its scheduler with another busy warp (measured: 190 -> 335 clk per step), so
     // the compute warps take schedulers 0..wpc-1 (first row of warps) and the writers and the
     // loader are spread over the other schedulers; the remaining warp slots exit at once.
     const int sched = wid & 3, wrow = wid >> 2;
     const int nserv = 4 - wpc;                                   // schedulers that serve writers / loader
-    const int nwriters = wpc * kWriters;
+    const int nwriters = STORE ? wpc * kWriters : 0;
     int role = -1;                                               // -1 idle, 0 compute, 1 writer, 2 loader
     int w = 0;                                                   // compute: strip in the band; writer: writer index
     if (sched < wpc) { if (wrow == 0) { role = 0; w = sched; } }
@@ -601,41 +636,52 @@ fill_kernel(const FillParams p)
         else if (slot == nwriters) role = 2;
     }
 
-    int4* stage4  = smem4;                                       // [wpc][kStripRows][kT]
-    int4* rings   = stage4 + (size_t)wpc * kStripRows * kT;      // [wpc][kRing]
-    int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc*kWriters][32]
+    int4* stage4  = smem4;                                       // [wpc][kStripRows][KT]   (STORE only)
+    int4* rings   = stage4 + (STORE ? (size_t)wpc * kStripRows * KT : 0);   // [wpc][kRing]
+    int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc*kWriters][32]      (STORE only)
 
-    if (threadIdx.x == 0) s_band = atomicAdd(p.ticket, 1);
+    if (threadIdx.x == 0) s_band = atomicAdd(p_in.ticket, 1);
     if (threadIdx.x < kMaxWpc) s_staged[threadIdx.x] = 0;
     if (threadIdx.x < kMaxWpc * kWriters) s_drained[threadIdx.x] = 0;
     if (threadIdx.x <= kMaxWpc) s_consumed[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < wpc * kRing; i += blockDim.x) rings[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
-    const int band = s_band;
+    // tickets are handed out pair by pair, band by band: a waiting band's predecessor is resident
+    const long long pair = s_band / p_in.nbands;
+    const int band = s_band % p_in.nbands;
+    FillParams p = p_in;
+    p.a4 += pair * p.a4_stride;
+    p.b += pair * p.n;
+    p.H += pair * p.pair_stride; p.P += pair * p.pair_stride;
+    p.boundary += pair * (long long)(p.nbands - 1) * p.bstride;
+    p.strip_max += pair * p.nstrips;
+    p.gmax += pair;
+    if (!STORE) p.row_best += pair * (p.n + 1);
     const long long band_r0 = 1 + (long long)band * wpc * kStripRows;
 
     if (role == 0) {
         // ------------------------------------------------ compute
         const long long r0 = band_r0 + (long long)kStripRows * w;
         if (r0 > p.n) return;
-        Strip S;
+        Strip<KT, STORE> S;
         S.lane = lane;
 #pragma unroll
         for (int q = 0; q < kR; ++q) {
             const long long row = r0 + kR * lane + q;
             S.b4[q] = (row <= p.n) ? (unsigned)p.b[row - 1] * 0x01010101u : 0u;
-            S.hl[q] = 0;
+            S.hl[q] = 0; S.rmax[q] = 0; S.rcol[q] = 0;
         }
         // keep the scoring constants in registers: a shuffle result is opaque to ptxas, which
         // otherwise re-reads them from the constant bank at the head of every step, on the
         // dependency chain
         S.sm = opaque(p.s_match); S.sx = opaque(p.s_mismatch); S.gu = opaque(p.g_up); S.gl = opaque(p.g_left);
         S.A0 = S.A1 = S.A2 = S.A3 = 0; S.dgp = 0;
-        S.sa_base = (unsigned)__cvta_generic_to_shared(stage4 + ((size_t)w * kStripRows + (size_t)kR * lane) * kT);
-        S.sa = S.sa_base + 16u * (unsigned)lane;                 // slot (t + lane) & (kT-1) at t = 0
+        S.sa_base = (unsigned)__cvta_generic_to_shared(stage4 + ((size_t)w * kStripRows + (size_t)kR * lane) * KT);
+        S.sa = S.sa_base + 16u * (unsigned)lane;                 // slot (t + lane) & (KT-1) at t = 0
         S.ring_in  = (unsigned)__cvta_generic_to_shared(rings + (size_t)w * kRing);
         S.ring_out = (unsigned)__cvta_generic_to_shared(rings + (size_t)(w + 1 < wpc ? w + 1 : w) * kRing);
         S.jmax = p.jmax;
+        S.mcols = (int)p.m;
         S.has_in = opaque(r0 > 1 ? 1 : 0);
         const bool next_row = (r0 + kStripRows <= p.n);          // a strip below exists
         const bool ring_consumer = next_row && (w + 1 < wpc);
@@ -645,17 +691,31 @@ fill_kernel(const FillParams p)
         // step index is an immediate (only lane 31's copy is ever dereferenced, from t = 31 on)
         S.gout = p.boundary + (size_t)(next_row && (w + 1 == wpc) ? band : 0) * p.bstride - lane;
         const unsigned* aw = p.a4 + kAPad - lane;                // aw[t] = characters of block t - lane
-        compute_strip(p, S, aw, (unsigned)__cvta_generic_to_shared(s_staged + w),
+        const long long strip = (r0 - 1) / kStripRows;
+        compute_strip<KT, STORE>(p, S, aw, (unsigned)__cvta_generic_to_shared(s_staged + w),
                       (unsigned)__cvta_generic_to_shared(s_drained + w * kWriters),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w),
-                      (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, (r0 - 1) / kStripRows);
+                      (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, strip + pair * p.nstrips);
+        if (!STORE) {
+            // per-row best cells and the strip / global maxima (maxPos is reduced from them)
+            int mx = 0;
+#pragma unroll
+            for (int q = 0; q < kR; ++q) {
+                const long long row = r0 + kR * lane + q;
+                if (row <= p.n)
+                    p.row_best[row] = ((unsigned long long)(unsigned)(S.rmax[q] >> 4) << 32) | (0xffffffffu - (unsigned)S.rcol[q]);
+                if (row <= p.n) mx = max(mx, S.rmax[q] >> 4);
+            }
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0 && mx > 0) { atomicMax(p.strip_max + strip, mx); atomicMax(p.gmax, mx); }
+        }
     } else if (role == 1) {
         // ------------------------------------------------ writer
         const int wi = w;                                        // writer index in the CTA
         const int cw = wi / kWriters, sub = wi % kWriters;
         const long long r0 = band_r0 + (long long)kStripRows * cw;
         if (r0 > p.n) return;                                    // (a writer without valid rows still runs: it owns a drained flag)
-        writer_strip(p, r0, sub, lane, reinterpret_cast<const int*>(stage4 + (size_t)cw * kStripRows * kT),
+        writer_strip<KT>(p, r0, sub, lane, reinterpret_cast<const int*>(stage4 + (size_t)cw * kStripRows * KT),
                      rowtabs + (size_t)wi * 32, s_staged + cw, s_drained + wi,
                      (r0 - 1) / kStripRows);
     } else if (role == 2) {
@@ -665,23 +725,61 @@ fill_kernel(const FillParams p)
     }
 }
 
+// score-only: maxPos from the per-row best cells -- among the rows whose best score equals the
+// global maximum, the cell with the smallest i+j, then the largest i (the row's first column
+// with that score is its earliest anti-diagonal).  One block per pair.
+__global__ void rowbest_argmax_kernel(const unsigned long long* __restrict__ row_best, long long n, long long pitch,
+                                      const int* __restrict__ gmax, long long* maxPos, int32_t* maxScore)
+{
+    const long long pair = blockIdx.x;
+    row_best += pair * (n + 1);
+    const int g = gmax[pair];
+    __shared__ unsigned long long s_key;
+    if (threadIdx.x == 0) s_key = ~0ull;
+    __syncthreads();
+    if (g > 0) {
+        unsigned long long best = ~0ull;
+        for (long long r = 1 + threadIdx.x; r <= n; r += blockDim.x) {
+            const unsigned long long v = row_best[r];
+            if ((int)(v >> 32) == g) {
+                const long long col = (long long)(0xffffffffu - (unsigned)(v & 0xffffffffu));
+                const unsigned long long k = ((unsigned long long)(r + col) << 32) | (unsigned long long)(0xffffffffu - (unsigned)r);
+                best = k < best ? k : best;
+            }
+        }
+        atomicMin(&s_key, best);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long pos = 0;
+        if (g > 0) {
+            const long long r = (long long)(0xffffffffu - (unsigned)(s_key & 0xffffffffu));
+            pos = r * pitch + ((long long)(s_key >> 32) - r);
+        }
+        if (maxPos) maxPos[pair] = pos;
+        if (maxScore) maxScore[pair] = g;
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // maxPos with the reference's tie-break: among the cells with H == global max, the one
 // with the smallest i+j, then the largest i (omp_smithW.c:203-215,282-291,384-387).
 // Only rows of strips whose maximum equals the global maximum are scanned.
 // ---------------------------------------------------------------------------------
-__global__ void argmax_kernel(const int32_t* __restrict__ H, long long pitch, long long m, long long n,
+__global__ void argmax_kernel(const int32_t* __restrict__ H, long long pitch, long long pair_stride, long long m, long long n,
                               const int* __restrict__ strip_max, const int* __restrict__ gmax,
                               unsigned long long* key)
 {
-    const int g = *gmax;
+    const long long pair = blockIdx.y;
+    const long long nstrips = (n + kStripRows - 1) / kStripRows;
+    H += pair * pair_stride; strip_max += pair * nstrips; key += pair;
+    const int g = gmax[pair];
     if (g <= 0) return;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     constexpr int kChunk = 1024;                                   // columns per work item
     const long long nchunks = (m + kChunk - 1) / kChunk;
-    const long long nstrips = (n + kStripRows - 1) / kStripRows;
     // work item = (strip, row in strip, column chunk); strips that do not attain the maximum are skipped whole
     for (long long st = 0; st < nstrips; ++st) {
         if (strip_max[st] != g) continue;
@@ -709,19 +807,21 @@ __global__ void argmax_kernel(const int32_t* __restrict__ H, long long pitch, lo
     }
 }
 
-__global__ void finalize_kernel(const unsigned long long* key, const int* gmax, long long pitch,
+__global__ void finalize_kernel(const unsigned long long* key, const int* gmax, long long pitch, long long npairs,
                                 long long* maxPos, int32_t* maxScore)
 {
-    const int g = *gmax;
+    const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= npairs) return;
+    const int g = gmax[pair];
     long long pos = 0;
     if (g > 0) {
-        const unsigned long long k = *key;
+        const unsigned long long k = key[pair];
         const long long r = (long long)(0xffffffffu - (unsigned)(k & 0xffffffffu));
         const long long j = (long long)(k >> 32) - r;
         pos = r * pitch + j;
     }
-    if (maxPos) *maxPos = pos;
-    if (maxScore) *maxScore = g;
+    if (maxPos) maxPos[pair] = pos;
+    if (maxScore) maxScore[pair] = g;
 }
 
 // ---------------------------------------------------------------------------------

@@ -185,3 +185,49 @@ def test_medium_blockwise(swb, oracle, cols, rows, seed):
     leno = oracle.backtrack(Pfull, maxPos)
     assert swb.backtrack(dP, cols + 1, maxPos) == leno
     assert (Pv.cpu().numpy() == Pfull).all()
+
+
+def test_score_only_kernel(swb, oracle):
+    # no H/P stores: max score and maxPos (reference tie-break) from the per-row best cells
+    rng = np.random.default_rng(21)
+    for (m, n) in [(8, 9), (1, 1), (77, 130), (300, 64), (1027, 700), (4100, 1500), (700, 4100)]:
+        a, b = rng.choice(ACGT, m), rng.choice(ACGT, n)
+        ms, mp = swb.score_only(bytes(a), bytes(b))
+        mso, mpo = oracle.score_only(a, b)
+        assert (ms, mp) == (mso, mpo), (m, n)
+    for seed in range(40):                      # tie-heavy shape
+        a, b = oracle.generate(2000 + seed, 256, 256)
+        assert swb.score_only(bytes(a), bytes(b)) == oracle.score_only(a, b), seed
+    # no positive score
+    assert swb.score_only(b"A" * 100, b"C" * 90) == (0, 0)
+
+
+@pytest.mark.parametrize("m,n,npairs", [(256, 256, 96), (100, 70, 33), (513, 130, 17)])
+def test_batch_of_pairs(swb, oracle, m, n, npairs):
+    # BASELINE config 5 in small: independent equally shaped pairs in one launch
+    rng = np.random.default_rng(m + n)
+    A = rng.choice(ACGT, (npairs, m)); B = rng.choice(ACGT, (npairs, n))
+    pitch = m + 1
+    stride = ((n + 1) * pitch + 3) // 4 * 4
+    dev = torch.device("cuda:0")
+    dH = torch.full((npairs * stride,), -999, dtype=torch.int32, device=dev)
+    dP = torch.full((npairs * stride,), -999, dtype=torch.int32, device=dev)
+    d_pos = torch.zeros(npairs, dtype=torch.int64, device=dev)
+    d_sc = torch.zeros(npairs, dtype=torch.int32, device=dev)
+    swb.fill_batch_async(np.ascontiguousarray(A), m, np.ascontiguousarray(B), n, npairs, dH, dP, pitch, stride, d_pos, d_sc,
+                         stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    Hh = dH.view(npairs, stride).cpu().numpy(); Ph = dP.view(npairs, stride).cpu().numpy()
+    pos = d_pos.cpu().numpy(); scs = d_sc.cpu().numpy()
+    for k in range(npairs):
+        Ho, Po, mpo = oracle.fill(A[k], B[k])
+        assert (Hh[k, :(n + 1) * pitch].reshape(n + 1, pitch) == Ho).all(), k
+        assert (Ph[k, :(n + 1) * pitch].reshape(n + 1, pitch) == Po).all(), k
+        assert pos[k] == mpo and scs[k] == Ho.max(), k
+        assert (Hh[k, (n + 1) * pitch:] == -999).all()
+    # score-only batch agrees
+    d_pos2 = torch.zeros(npairs, dtype=torch.int64, device=dev); d_sc2 = torch.zeros(npairs, dtype=torch.int32, device=dev)
+    swb.score_only_async(np.ascontiguousarray(A), m, np.ascontiguousarray(B), n, npairs, d_pos2, d_sc2,
+                         stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert (d_pos2.cpu().numpy() == pos).all() and (d_sc2.cpu().numpy() == scs).all()

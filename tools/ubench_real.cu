@@ -57,7 +57,8 @@ __global__ void k(const unsigned* aw_, int ngroups, long long* out_clk, int* sin
     }
     for (int i = lane; i < 2 * kRing; i += 32) ring[i] = make_int4(0, 0, 0, 0);
     __syncwarp();
-    Strip S;
+    Strip<64, true> S;
+    constexpr int kT = 64, kRowInts = 256;
     S.lane = lane;
     for (int q = 0; q < kR; ++q) { S.b4[q] = 0x41414141u + 0x01010101u * ((lane + q) & 3); S.hl[q] = 0; }
     S.sm = opaque(16 * 3 + 7); S.sx = opaque(16 * -3 + 7); S.gu = opaque(16 * -2 + 5); S.gl = opaque(16 * -2 + 2);
