@@ -89,9 +89,9 @@ void keep_pool_warm(int device)
     done[device] = true;
 }
 
-int pick_wpc(int64_t n, int kt, bool store, const swb_tuning* tuning)
+int pick_wpc(int64_t n, int64_t npairs, int kt, bool store, const swb_tuning* tuning)
 {
-    int wpc = 2;
+    int wpc = (npairs > 1) ? 1 : 2;         // measured: 65536 x 256x256 pairs 295 vs 247 GCUPS with 1 strip per CTA
     if (const char* e = std::getenv("SWB_WPC")) wpc = std::atoi(e);
     if (tuning && tuning->warps_per_band > 0) wpc = tuning->warps_per_band;
     wpc = std::max(1, std::min(wpc, swb::kMaxWpc));
@@ -104,7 +104,9 @@ int pick_wpc(int64_t n, int kt, bool store, const swb_tuning* tuning)
 template <int KT, bool STORE>
 cudaError_t launch_fill(const swb::FillParams& p, long long nblocks, int wpc, cudaStream_t st)
 {
-    const size_t smem = swb::fill_smem_bytes(wpc, KT, STORE);
+    // score-only needs 1 KB per strip but asks for the full-fill footprint of a large pair: one CTA per SM
+    // keeps waiting CTAs off the schedulers of the working ones (measured 13 ms -> see DESIGN.md)
+    const size_t smem = (!STORE && p.nbands > 8) ? swb::fill_smem_bytes(wpc, 64, true) : swb::fill_smem_bytes(wpc, KT, STORE);
     cudaError_t e = cudaFuncSetAttribute(swb::fill_kernel<KT, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     swb::fill_kernel<KT, STORE><<<(unsigned)nblocks, swb::fill_block_threads(wpc, STORE), smem, st>>>(p);
@@ -134,7 +136,7 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
 
     // single large pairs: deep staging ring, one CTA per SM; batches of small pairs: shallow ring, more CTAs per SM
     const int kt = (npairs > 1) ? 32 : 64;
-    const int wpc = pick_wpc(n, kt, store, tuning);
+    const int wpc = pick_wpc(n, npairs, kt, store, tuning);
     const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
     const int nbands = (int)((strips + wpc - 1) / wpc);
     if ((long long)nbands * npairs >= (1LL << 31)) return SWB_ERR_RANGE;
@@ -216,7 +218,7 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
 
         if (store) {
             const int am_blocks = (npairs > 1) ? 1 : (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
-            swb::argmax_kernel<<<dim3((unsigned)am_blocks, (unsigned)npairs), 256, 0, st>>>(dH, pitch, pair_stride, m, n, ws.strip_max,
+            swb::argmax_kernel<<<dim3((unsigned)npairs, (unsigned)am_blocks), 256, 0, st>>>(dH, pitch, pair_stride, m, n, ws.strip_max,
                                                                                               ws.gmax, ws.key);
             SWB_CUDA(cudaGetLastError());
             swb::finalize_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(ws.key, ws.gmax, pitch, npairs,

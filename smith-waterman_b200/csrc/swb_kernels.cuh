@@ -421,6 +421,14 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 #ifdef SWB_X_GROUPTRACE
         const long long gc1 = clock64();
 #endif
+        // Score only: nothing throttles the strips (the writers' back-pressure does that in the full
+        // fill), so every strip would run flush against its producer and pay a failed early poll plus
+        // a spin loop in every step.  Waiting once per group for the LAST block this group needs
+        // keeps all eight polls on the fast path.
+        if (!STORE && S.has_in && t0 + 8 <= p.jmax) {
+            int x = lds_volatile_int4<0>(in_w).x;
+            while ((x & 3) != want_w) x = lds_volatile_int4<0>(in_w).x;
+        }
 #define SWB_STEP(E, I) S.template step<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w)
         if (g >= 4 && g <= gtail) {
             SWB_STEP(false, 0); SWB_STEP(false, 1); SWB_STEP(false, 2); SWB_STEP(false, 3);
@@ -624,7 +632,14 @@ fill_kernel(const FillParams p_in)
     // not share its scheduler with another busy warp (measured: 190 -> 335 clk per step), so
     // the compute warps take schedulers 0..wpc-1 (first row of warps) and the writers and the
     // loader are spread over the other schedulers; the remaining warp slots exit at once.
-    const int sched = wid & 3, wrow = wid >> 2;
+    // Several CTAs can share an SM (batches, score-only): consecutive bands rotate the scheduler
+    // assignment so that their compute warps land on different schedulers.
+    if (threadIdx.x == 0) s_band = atomicAdd(p_in.ticket, 1);
+    if (threadIdx.x < kMaxWpc) s_staged[threadIdx.x] = 0;
+    if (threadIdx.x < kMaxWpc * kWriters) s_drained[threadIdx.x] = 0;
+    if (threadIdx.x <= kMaxWpc) s_consumed[threadIdx.x] = 0;
+    __syncthreads();
+    const int sched = ((wid & 3) + 4 - ((s_band * wpc) & 3)) & 3, wrow = wid >> 2;
     const int nserv = 4 - wpc;                                   // schedulers that serve writers / loader
     const int nwriters = STORE ? wpc * kWriters : 0;
     int role = -1;                                               // -1 idle, 0 compute, 1 writer, 2 loader
@@ -640,10 +655,6 @@ fill_kernel(const FillParams p_in)
     int4* rings   = stage4 + (STORE ? (size_t)wpc * kStripRows * KT : 0);   // [wpc][kRing]
     int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc*kWriters][32]      (STORE only)
 
-    if (threadIdx.x == 0) s_band = atomicAdd(p_in.ticket, 1);
-    if (threadIdx.x < kMaxWpc) s_staged[threadIdx.x] = 0;
-    if (threadIdx.x < kMaxWpc * kWriters) s_drained[threadIdx.x] = 0;
-    if (threadIdx.x <= kMaxWpc) s_consumed[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < wpc * kRing; i += blockDim.x) rings[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
     // tickets are handed out pair by pair, band by band: a waiting band's predecessor is resident
@@ -770,14 +781,14 @@ __global__ void argmax_kernel(const int32_t* __restrict__ H, long long pitch, lo
                               const int* __restrict__ strip_max, const int* __restrict__ gmax,
                               unsigned long long* key)
 {
-    const long long pair = blockIdx.y;
+    const long long pair = blockIdx.x;                             // grid = (pairs, blocks per pair)
     const long long nstrips = (n + kStripRows - 1) / kStripRows;
     H += pair * pair_stride; strip_max += pair * nstrips; key += pair;
     const int g = gmax[pair];
     if (g <= 0) return;
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long warp = ((long long)blockIdx.y * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.y * blockDim.x) >> 5;
     constexpr int kChunk = 1024;                                   // columns per work item
     const long long nchunks = (m + kChunk - 1) / kChunk;
     // work item = (strip, row in strip, column chunk); strips that do not attain the maximum are skipped whole
