@@ -116,9 +116,14 @@ cudaError_t launch_fill(const swb::FillParams& p, long long nblocks, int wpc, cu
 // The one implementation behind swb_fill_async, swb_fill_batch_async and swb_score_only_async.
 //   npairs equally shaped pairs: a = npairs*m bytes, b = npairs*n bytes, pair k's matrices at
 //   dH/dP + k*pair_stride; d_maxPos / d_maxScore hold npairs entries.  store == false: score only.
+struct StripLink {                         // column-strip mode (nullptr members = not used)
+    const int32_t* left_in = nullptr; const int* left_flags = nullptr;
+    int32_t* right_out = nullptr; int* right_flags = nullptr; int epoch = 0;
+};
+
 int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs, const swb_scoring* scoring,
               int32_t* dH, int32_t* dP, int64_t pitch, int64_t pair_stride, int64_t* d_maxPos, int32_t* d_maxScore,
-              int device, void* stream, const swb_tuning* tuning, bool store)
+              int device, void* stream, const swb_tuning* tuning, bool store, const StripLink* link = nullptr)
 {
     if (!a || !b || m <= 0 || n <= 0 || npairs <= 0) return SWB_ERR_ARG;
     if (store && (!dH || !dP || pitch < m + 1)) return SWB_ERR_ARG;
@@ -206,6 +211,8 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
         p.trace = tuning ? reinterpret_cast<unsigned long long*>(tuning->trace) : nullptr;
         p.nbands = nbands; p.nstrips = strips; p.a4_stride = ws.a4_words; p.pair_stride = pair_stride;
         p.row_best = ws.row_best;
+        if (link) { p.left_in = link->left_in; p.left_flags = link->left_flags; p.right_out = link->right_out;
+                    p.right_flags = link->right_flags; p.epoch = link->epoch; }
         swb_timer* timer = tuning ? tuning->timer : nullptr;
         if (timer) SWB_CUDA(cudaEventRecord(timer->start, st));
         const long long nblocks = (long long)nbands * npairs;
@@ -332,6 +339,68 @@ int swb_fill_batch_async(const char* a, int64_t m, const char* b, int64_t n, int
                      tuning, true);
 }
 
+int swb_fill_strip_async(const char* a_local, int64_t m_local, const char* b, int64_t n,
+                         const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch,
+                         const int32_t* left_in, const int32_t* left_flags, int32_t* right_out, int32_t* right_flags,
+                         int32_t epoch, int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream,
+                         const swb_tuning* tuning)
+{
+    if ((left_in == nullptr) != (left_flags == nullptr) || (right_out == nullptr) != (right_flags == nullptr) || epoch == 0)
+        return SWB_ERR_ARG;
+    StripLink link;
+    link.left_in = left_in; link.left_flags = left_flags; link.right_out = right_out; link.right_flags = right_flags;
+    link.epoch = epoch;
+    return fill_impl(a_local, m_local, b, n, 1, scoring, dH, dP, pitch, 0, d_maxPos, d_maxScore, device, stream, tuning, true,
+                     &link);
+}
+
+void* swb_ipc_alloc(size_t bytes, int device)
+{
+    DeviceGuard guard(device);
+    void* p = nullptr;
+    if (!guard.ok || cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
+    return p;
+}
+void swb_ipc_free(void* p, int device) { DeviceGuard guard(device); if (p) cudaFree(p); }
+int swb_ipc_get_handle(void* p, unsigned char* out64)
+{
+    if (!p || !out64) return SWB_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    SWB_CUDA(cudaIpcGetMemHandle(&h, p));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(out64, &h, 64);
+    return SWB_OK;
+}
+int swb_ipc_open(const unsigned char* handle64, int device, void** out)
+{
+    if (!handle64 || !out) return SWB_ERR_ARG;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    SWB_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SWB_OK;
+}
+int swb_ipc_close(void* p, int device)
+{
+    DeviceGuard guard(device);
+    if (p) SWB_CUDA(cudaIpcCloseMemHandle(p));
+    return SWB_OK;
+}
+int swb_enable_peer(int device, int peer)
+{
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    int can = 0;
+    SWB_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return SWB_ERR_ARG;
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __LINE__);
+    cudaGetLastError();
+    return SWB_OK;
+}
+
 int swb_score_only_async(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs,
                          const swb_scoring* scoring, int64_t* d_maxPos, int32_t* d_maxScore,
                          int device, void* stream, const swb_tuning* tuning)
@@ -362,6 +431,21 @@ int swb_fill(const char* a, int64_t m, const char* b, int64_t n,
     return rc;
 }
 
+int swb_backtrack_from_async(int32_t* dP, int64_t pitch, int64_t startPos, int64_t* d_pathLen, int64_t* d_endPos,
+                             int device, void* stream)
+{
+    if (!dP || pitch <= 1 || startPos < 0) return SWB_ERR_ARG;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int bt_smem = (2 * (swb::kBtPad + swb::kBtBandInts) + 2 * swb::kBtList) * (int)sizeof(int);
+    SWB_CUDA(cudaFuncSetAttribute(swb::backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt_smem));
+    swb::backtrack_kernel<<<1, swb::kBtThreads, bt_smem, st>>>(dP, pitch, startPos, nullptr, reinterpret_cast<long long*>(d_pathLen),
+                                                               reinterpret_cast<long long*>(d_endPos));
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+
 int swb_backtrack_async(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_t* d_maxPos,
                         int64_t* d_pathLen, int device, void* stream)
 {
@@ -372,7 +456,7 @@ int swb_backtrack_async(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_
     const int bt_smem = (2 * (swb::kBtPad + swb::kBtBandInts) + 2 * swb::kBtList) * (int)sizeof(int);
     SWB_CUDA(cudaFuncSetAttribute(swb::backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt_smem));
     swb::backtrack_kernel<<<1, swb::kBtThreads, bt_smem, st>>>(dP, pitch, maxPos, reinterpret_cast<const long long*>(d_maxPos),
-                                            reinterpret_cast<long long*>(d_pathLen));
+                                            reinterpret_cast<long long*>(d_pathLen), nullptr);
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;
 }

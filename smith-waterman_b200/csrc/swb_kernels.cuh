@@ -70,6 +70,7 @@ __host__ __device__ constexpr int stage_slack(int KT) { return KT / kGroup - 2; 
 // tie codes: larger wins on equal score => NONE > DIAGONAL > UP > LEFT, and code&3 is
 // the reference's P value (omp_smithW.c:33-36)
 constexpr int kTieNone = 8, kTieDiag = 7, kTieUp = 5, kTieLeft = 2;
+constexpr int kHandOff = 5;            // P code of local column 0 in column-strip mode (not a reference code)
 
 struct FillParams {
     const unsigned* a4;      // a4[kAPad + j] = a[4j-1 .. 4j+2] (block j; 0 outside [0,m))
@@ -96,6 +97,13 @@ struct FillParams {
     long long       a4_stride, pair_stride;
     // score-only mode (no H/P stores): per-row best cell, packed (score << 32) | (0xffffffff - column)
     unsigned long long* row_best;
+    // column-strip mode (one GPU of several working on one pair): this GPU owns columns c0+1..c0+m of
+    // the pair; local column 0 is the last column of the GPU to the left.
+    const int32_t*  left_in;               // [n+1] H of that column (written by the left GPU), or nullptr
+    const int*      left_flags;            // [nstrips] == epoch once the 64 rows of a strip are in left_in
+    int32_t*        right_out;             // PEER pointer: the right GPU's left_in, or nullptr
+    int*            right_flags;           // PEER pointer: the right GPU's left_flags
+    int             epoch;
 };
 
 __device__ __forceinline__ void trace_stamp(const FillParams& p, long long strip, int slot, int lane)
@@ -149,6 +157,10 @@ __device__ __forceinline__ void st_cg_int4_if(const int4* p, const int4& v, int 
 {
     asm volatile("{ .reg .pred q; setp.ne.s32 q, %5, 0; @q st.global.cg.v4.s32 [%0+%6], {%1,%2,%3,%4}; }"
                  ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(on), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ void st_cg_int_if(int32_t* p, int v, int on)
+{
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.global.cg.s32 [%0], %1; }" ::"l"(p), "r"(v), "r"(on) : "memory");
 }
 template <int OFF>
 __device__ __forceinline__ void sts_int4(unsigned a, int x, int y, int z, int w)
@@ -231,6 +243,9 @@ struct Strip {
     int   out_ring, out_glob;     // THIS LANE hands blocks on (lane 31 only): to the ring / to global
     int   jmax;
     int   mcols;                  // m
+    int   lbk[kR];                // packed key of my rows' local column 0: NONE, or 16*H of the left GPU's last column
+    int32_t* rout;                // right_out + my first row (column-strip mode) or nullptr
+    int   rsel;                   // m & 3: element of block jmax that is my last column
     int   rmax[kR], rcol[kR];     // score-only: best clean 16*H of each of my rows and its first column
 
     __device__ __forceinline__ void scores(const unsigned aword)
@@ -280,7 +295,7 @@ struct Strip {
             const int t3 = __viaddmax_s32(u3, gu, p3);
             dg = hl[q];                                  // diagonal of the next row's first cell
             int k0 = __viaddmax_s32(hl[q], gl, t0);
-            if (EDGE) { if (j <= 0) k0 = kTieNone; }
+            if (EDGE) { if (j <= 0) k0 = (j == 0) ? lbk[q] : kTieNone; }
             const int h0 = k0 & ~15;
             if (q == kR - 1) n0 = __shfl_up_sync(0xffffffffu, h0, 1);
             int k1 = __viaddmax_s32(h0, gl, t1);
@@ -296,6 +311,11 @@ struct Strip {
             const int h3 = k3 & ~15;
             if (q == kR - 1) n3 = __shfl_up_sync(0xffffffffu, h3, 1);
             hl[q] = h3;
+            if (EDGE && STORE) {
+                // column-strip mode: my last column (block jmax) goes to the GPU on the right (P2P store)
+                const int he = (rsel == 0) ? h0 : (rsel == 1) ? h1 : (rsel == 2) ? h2 : h3;
+                st_cg_int_if(rout + q, he >> 4, (rout != nullptr && j == jmax) ? 1 : 0);
+            }
             if (STORE) {
                 // stage the packed block of this row for the writers
                 if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
@@ -460,6 +480,15 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
     }
     return;
 #endif
+    if (STORE && p.right_flags != nullptr) {
+        // every lane's boundary stores are ordered before the flag (system scope: another GPU reads them)
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            int* f = p.right_flags + (strip % p.nstrips);
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(p.epoch) : "memory");
+        }
+    }
     trace_stamp(p, strip, 4, lane);
 }
 
@@ -489,8 +518,9 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
     const unsigned long long hb = (unsigned long long)(p.H + G0);
     rowtab[lane] = make_int4((int)(unsigned)hb, (int)(unsigned)(hb >> 32), F, E);
     const unsigned rowmask = __ballot_sync(0xffffffffu, row <= p.n);
-    const int Emax = __reduce_max_sync(0xffffffffu, E);
-    const int Emin = __reduce_min_sync(0xffffffffu, E);
+    const int nvalid = __popc(rowmask);
+    const int Emax = __reduce_max_sync(0xffffffffu, row <= p.n ? E : 0);
+    const int Emin = __reduce_min_sync(0xffffffffu, row <= p.n ? E : 0x7fffffff);
     __syncwarp();
     const int* mystage = stage + (size_t)32 * sub * kRowInts;
 
@@ -515,8 +545,9 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
         const long long wc1 = clock64();
 #endif
         const int v = 32 * r + lane;
-        const bool interior = (rowmask == 0xffffffffu) && (32 * r - Emax >= 0) && (32 * r + 31 - Emin <= m);
-        if (interior) {
+        // (the valid rows of a strip are its first nvalid ones: the last strip of a pair may be partial)
+        const bool interior = (32 * r - Emax >= (p.left_in != nullptr ? 1 : 0)) && (32 * r + 31 - Emin <= m);
+        if (interior && nvalid == 32) {
             // batches of 8 rows: all table and data loads first, then the 16 stores
 #pragma unroll 1
             for (int l0 = 0; l0 < 32; l0 += 8) {
@@ -538,6 +569,17 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                     mx = max(mx, k[i]);
                 }
             }
+        } else if (interior) {
+            // partial strip (the last one of a pair): same, row by row
+#pragma unroll 2
+            for (int l = 0; l < nvalid; ++l) {
+                const int4 tb = rowtab[l];
+                int32_t* hp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.y << 32) | (unsigned)tb.x) + v;
+                const int k = mystage[l * kRowInts + ((v + tb.z) & (kRowInts - 1))];
+                __stcs(hp, k >> 4);
+                __stcs(hp + pdelta, k & 3);
+                mx = max(mx, k);
+            }
         } else {
 #pragma unroll 2
             for (int l = 0; l < 32; ++l) {
@@ -548,8 +590,10 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                     const int k = mystage[l * kRowInts + idx];
                     int32_t* hp = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.y << 32) | (unsigned)tb.x) + v;
                     __stcs(hp, k >> 4);
-                    __stcs(hp + pdelta, k & 3);
-                    mx = max(mx, k);
+                    // column-strip mode: local column 0 belongs to the GPU on the left; its P holds the
+                    // hand-off marker that ends this GPU's part of the backtrack
+                    __stcs(hp + pdelta, (c == 0 && p.left_in != nullptr) ? kHandOff : (k & 3));
+                    if (c > 0 || p.left_in == nullptr) mx = max(mx, k);
                 }
             }
         }
@@ -693,6 +737,27 @@ fill_kernel(const FillParams p_in)
         S.ring_out = (unsigned)__cvta_generic_to_shared(rings + (size_t)(w + 1 < wpc ? w + 1 : w) * kRing);
         S.jmax = p.jmax;
         S.mcols = (int)p.m;
+        S.rsel = (int)(p.m & 3);
+        S.rout = (STORE && p.right_out != nullptr) ? p.right_out + r0 + kR * lane : nullptr;
+        if (STORE && p.left_in != nullptr) {
+            // column-strip mode: the 64 boundary values of this strip come from the GPU on the left
+            const int* f = p.left_flags + (r0 - 1) / kStripRows;
+            int v;
+            do {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v != p.epoch) __nanosleep(200);
+            } while (v != p.epoch);
+#pragma unroll
+            for (int q = 0; q < kR; ++q) {
+                const long long row = r0 + kR * lane + q;
+                int hv = 0;
+                if (row <= p.n) asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(hv) : "l"(p.left_in + row) : "memory");
+                S.lbk[q] = 16 * hv;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < kR; ++q) S.lbk[q] = kTieNone;
+        }
         S.has_in = opaque(r0 > 1 ? 1 : 0);
         const bool next_row = (r0 + kStripRows <= p.n);          // a strip below exists
         const bool ring_consumer = next_row && (w + 1 < wpc);
@@ -917,13 +982,13 @@ __device__ __forceinline__ void bt_writeback(const int* buf, const int* list, in
 
 __global__ void __launch_bounds__(kBtThreads)
 backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
-                 const long long* d_maxPos, long long* d_pathLen)
+                 const long long* d_maxPos, long long* d_pathLen, long long* d_endPos)
 {
     extern __shared__ __align__(16) int bt_smem[];      // 2 x (pad + 128x132 ints), then 2 lists
     __shared__ long long s_len;
     __shared__ int s_done, s_a, s_count[2];
     const long long pos = d_maxPos ? *d_maxPos : maxPos_arg;
-    if (pos <= 0) { if (threadIdx.x == 0 && d_pathLen) *d_pathLen = 0; return; }
+    if (pos <= 0) { if (threadIdx.x == 0) { if (d_pathLen) *d_pathLen = 0; if (d_endPos) *d_endPos = 0; } return; }
     long long i = pos / pitch, j = pos % pitch;         // current cell
     // the path only moves up and left: nothing after the end of the start row is ever needed (or read)
     const long long limit = (i + 1) * pitch;
@@ -1000,7 +1065,6 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
         __syncthreads();
 #endif
         pbi = bi; pbc = bc; have_prev = true;
-        if (s_done) break;
         {
             const int a = s_a;
             const int rr = (a + kBtRS) / kBtRS - 1;               // -1 = the marker row above the band
@@ -1009,6 +1073,7 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
             const long long g = s + (a - rr * kBtRS - (int)(s & 3));
             i = r; j = g - r * pitch;
         }
+        if (s_done) break;                                        // (i, j) = the cell that ended the walk
         // usable prefetch: the walk left through the top and enters the next band well inside it
         const long long kn = j - (nc - kBtCols / 2);              // its column in the next band's bottom row
         if (i == ni && kn >= 24 && kn <= kBtCols - 24) {
@@ -1035,6 +1100,7 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
     // the last band's path
     if (fetcher) bt_writeback(bandbuf(cur), listbuf(cur), s_count[cur], P, pitch, pbi, pbc);
     if (threadIdx.x == 0 && d_pathLen) *d_pathLen = s_len;
+    if (threadIdx.x == 0 && d_endPos) *d_endPos = i * pitch + j;
 #ifdef SWB_X_BTDEBUG
     if (threadIdx.x == 0) printf("backtrack: len %lld bands %d misses %d walk clk %lld total clk %lld\n", s_len, dbg_bands, dbg_miss, dbg_walk, clock64() - dbg_total0);
 #endif

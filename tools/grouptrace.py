@@ -1,7 +1,8 @@
 import importlib, sys, torch, numpy as np
 sys.path.insert(0, '.')
 swb = importlib.import_module("smith-waterman_b200")
-cols=rows=8192
+import os
+cols=rows=int(os.environ.get("SHAPE","8192"))
 wpc=int(sys.argv[1]) if len(sys.argv)>1 else 2
 SR=int(sys.argv[2]) if len(sys.argv)>2 else 64
 dev=torch.device("cuda:0")
