@@ -50,6 +50,9 @@ int check_scoring(const swb_scoring& sc, int64_t m, int64_t n)
     if (std::llabs((long long)sc.match) > lim || std::llabs((long long)sc.mismatch) > lim ||
         std::llabs((long long)sc.gap) > lim)
         return SWB_ERR_RANGE;
+    // a gap must cost something: the fill relies on H = 0 / NONE being what a cell with all-zero neighbours evaluates to
+    // (with gap >= 0 the scores are not bounded by match * min(m,n) either)
+    if (sc.gap >= 0) return SWB_ERR_RANGE;
     // packed keys are 16*H + tie in int32; H <= match * min(m,n)
     const int64_t hmax = (int64_t)std::max(sc.match, 0) * std::min(m, n);
     if (hmax >= (1LL << 26)) return SWB_ERR_RANGE;
@@ -140,7 +143,8 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
     keep_pool_warm(device);
 
     // single large pairs: deep staging ring, one CTA per SM; batches of small pairs: shallow ring, more CTAs per SM
-    const int kt = (npairs > 1) ? 32 : 64;
+    int kt = (npairs > 1) ? 32 : 64;
+    if (const char* e = std::getenv("SWB_KT")) kt = (std::atoi(e) == 32) ? 32 : 64;     // developer knob
     const int wpc = pick_wpc(n, npairs, kt, store, tuning);
     const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
     const int nbands = (int)((strips + wpc - 1) / wpc);

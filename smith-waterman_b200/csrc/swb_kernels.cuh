@@ -59,6 +59,10 @@ constexpr int kWriters  = kR;          // writer warps per strip, 32 rows each
 // row): 64 for single large pairs, 32 for batches of small pairs (more CTAs per SM)
 constexpr int kRing     = 64;          // hand-off ring capacity in blocks (power of two)
 constexpr int kGroup    = 8;           // steps per synchronisation group
+#ifndef SWB_WAIT_STEPS
+#define SWB_WAIT_STEPS 4
+#endif
+constexpr int kWaitSteps = SWB_WAIT_STEPS;   // steps per poll of the strip above (4 or 8)
 constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
 constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: compute warps on schedulers 0..wpc-1,
                                        // writers + loader on the others
@@ -70,6 +74,7 @@ __host__ __device__ constexpr int stage_slack(int KT) { return KT / kGroup - 2; 
 // tie codes: larger wins on equal score => NONE > DIAGONAL > UP > LEFT, and code&3 is
 // the reference's P value (omp_smithW.c:33-36)
 constexpr int kTieNone = 8, kTieDiag = 7, kTieUp = 5, kTieLeft = 2;
+constexpr int kSNeg = -(1 << 30);      // forced substitution score: the diagonal candidate cannot win (16*H < 2^30)
 constexpr int kHandOff = 5;            // P code of local column 0 in column-strip mode (not a reference code)
 
 struct FillParams {
@@ -100,7 +105,7 @@ struct FillParams {
     // column-strip mode (one GPU of several working on one pair): this GPU owns columns c0+1..c0+m of
     // the pair; local column 0 is the last column of the GPU to the left.
     const int32_t*  left_in;               // [n+1] H of that column (written by the left GPU), or nullptr
-    const int*      left_flags;            // [nstrips] == epoch once the 64 rows of a strip are in left_in
+    const int*      left_flags;            // [ceil(n/32)] == epoch once rows 32k+1..32k+32 are in left_in
     int32_t*        right_out;             // PEER pointer: the right GPU's left_in, or nullptr
     int*            right_flags;           // PEER pointer: the right GPU's left_flags
     int             epoch;
@@ -187,6 +192,19 @@ __device__ __forceinline__ void spin_until_ge(unsigned a, int want)
 #endif
     while (lds_volatile_int(a) < want) { }
 }
+// wait until block x of the strip above is in the hand-off ring (block x -> entry (x+32)&63, epoch tag 1 + ((x+32)>>6 & 1));
+// all lanes poll the same address
+__device__ __forceinline__ void wait_block(unsigned ring_in, int x)
+{
+    const unsigned a = ring_in + 16u * (unsigned)((x + 32) & (kRing - 1));
+    const int want = 1 + (((x + 32) >> 6) & 1);
+    int v = lds_volatile_int(a);
+    int spins = 0;
+    while ((v & 3) != want) {
+        if (++spins > 64) __nanosleep(20);
+        v = lds_volatile_int(a);
+    }
+}
 // a value the compiler / ptxas cannot rematerialise from the constant bank
 __device__ __forceinline__ int opaque(int x) { return __shfl_sync(0xffffffffu, x, 0); }
 
@@ -228,7 +246,7 @@ struct Strip {
     static constexpr int kRowInts = 4 * KT;
     int lane;
     unsigned b4[kR];              // my rows' characters, replicated in the four bytes
-    int sm, sx, gu, gl;
+    int sm, sx, gu, gl, g16;
     // dependency state (registers): block of the row above my first row for this step, its
     // last element of the previous step (diagonal of my first column), the last cell of
     // each of my rows
@@ -243,13 +261,15 @@ struct Strip {
     int   out_ring, out_glob;     // THIS LANE hands blocks on (lane 31 only): to the ring / to global
     int   jmax;
     int   mcols;                  // m
-    int   lbk[kR];                // packed key of my rows' local column 0: NONE, or 16*H of the left GPU's last column
-    int32_t* rout;                // right_out + my first row (column-strip mode) or nullptr
-    int   rsel;                   // m & 3: element of block jmax that is my last column
+    int   lb[kR];                 // 16*(H - gap) of my rows' local column 0 (column-strip mode: H of the left GPU's
+                                  // last column; otherwise 16*(0 - gap)): injected as the left neighbour of block 0
     int   rmax[kR], rcol[kR];     // score-only: best clean 16*H of each of my rows and its first column
 
     __device__ __forceinline__ void scores(const unsigned aword)
     {
+#ifdef SWB_X_NOSCORES
+        if (aword != 0x12345678u) return;          // timing experiment only: wrong results
+#endif
 #pragma unroll
         for (int q = 0; q < kR; ++q) {
             const unsigned x = aword ^ b4[q];
@@ -257,6 +277,22 @@ struct Strip {
             s[q][1] = (x & 0x0000ff00u) ? sx : sm;
             s[q][2] = (x & 0x00ff0000u) ? sx : sm;
             s[q][3] = (x & 0xff000000u) ? sx : sm;
+        }
+    }
+
+    // Head of a strip (first 4 groups): a lane has not started while its block index jn is negative,
+    // and column 0 (first cell of block 0) is the boundary column.  Nothing is forced on the dependency
+    // chain: with all inputs zero and the substitution score forced to kSNeg a cell evaluates to
+    // NONE / 0 by itself, and the boundary value of column 0 enters as the left neighbour.
+    __device__ __forceinline__ void head_fix(const int jn)
+    {
+#pragma unroll
+        for (int q = 0; q < kR; ++q) {
+            s[q][0] = (jn <= 0) ? kSNeg : s[q][0];
+            s[q][1] = (jn < 0) ? kSNeg : s[q][1];
+            s[q][2] = (jn < 0) ? kSNeg : s[q][2];
+            s[q][3] = (jn < 0) ? kSNeg : s[q][3];
+            hl[q] = (jn == 0) ? lb[q] : hl[q];
         }
     }
 
@@ -273,7 +309,6 @@ struct Strip {
         constexpr bool LAST = (I == kGroup - 1);
         const int j = t - lane;
         const bool poll = has_in && (!EDGE || t + 1 <= jmax);
-        const int  wnt  = LAST ? want_w : want;
         // block t+1 of the strip above (the row above lane 0's first row in the next step):
         // first try early, it is needed only after the shuffles
         int4 v = make_int4(0, 0, 0, 0);
@@ -294,28 +329,37 @@ struct Strip {
             const int t2 = __viaddmax_s32(u2, gu, p2);
             const int t3 = __viaddmax_s32(u3, gu, p3);
             dg = hl[q];                                  // diagonal of the next row's first cell
-            int k0 = __viaddmax_s32(hl[q], gl, t0);
-            if (EDGE) { if (j <= 0) k0 = (j == 0) ? lbk[q] : kTieNone; }
+#ifdef SWB_CLEAN_CHAIN
+            // the left-to-right chain carries clean 16*H values only: floor16(max(x + gl, T)) =
+            // max(x + 16*gap, floor16(T)) for x a multiple of 16, so the tie bits are masked off the chain
+            const int f0 = t0 & ~15, f1 = t1 & ~15, f2 = t2 & ~15, f3 = t3 & ~15;
+            const int h0 = __viaddmax_s32(hl[q], g16, f0);
+            if (q == kR - 1) n0 = __shfl_up_sync(0xffffffffu, h0, 1);
+            const int h1 = __viaddmax_s32(h0, g16, f1);
+            if (q == kR - 1) n1 = __shfl_up_sync(0xffffffffu, h1, 1);
+            const int h2 = __viaddmax_s32(h1, g16, f2);
+            if (q == kR - 1) n2 = __shfl_up_sync(0xffffffffu, h2, 1);
+            const int h3 = __viaddmax_s32(h2, g16, f3);
+            if (q == kR - 1) n3 = __shfl_up_sync(0xffffffffu, h3, 1);
+            const int k0 = __viaddmax_s32(hl[q], gl, t0);
+            const int k1 = __viaddmax_s32(h0, gl, t1);
+            const int k2 = __viaddmax_s32(h1, gl, t2);
+            const int k3 = __viaddmax_s32(h2, gl, t3);
+#else
+            const int k0 = __viaddmax_s32(hl[q], gl, t0);
             const int h0 = k0 & ~15;
             if (q == kR - 1) n0 = __shfl_up_sync(0xffffffffu, h0, 1);
-            int k1 = __viaddmax_s32(h0, gl, t1);
-            if (EDGE) { if (j < 0) k1 = kTieNone; }
+            const int k1 = __viaddmax_s32(h0, gl, t1);
             const int h1 = k1 & ~15;
             if (q == kR - 1) n1 = __shfl_up_sync(0xffffffffu, h1, 1);
-            int k2 = __viaddmax_s32(h1, gl, t2);
-            if (EDGE) { if (j < 0) k2 = kTieNone; }
+            const int k2 = __viaddmax_s32(h1, gl, t2);
             const int h2 = k2 & ~15;
             if (q == kR - 1) n2 = __shfl_up_sync(0xffffffffu, h2, 1);
-            int k3 = __viaddmax_s32(h2, gl, t3);
-            if (EDGE) { if (j < 0) k3 = kTieNone; }
+            const int k3 = __viaddmax_s32(h2, gl, t3);
             const int h3 = k3 & ~15;
             if (q == kR - 1) n3 = __shfl_up_sync(0xffffffffu, h3, 1);
+#endif
             hl[q] = h3;
-            if (EDGE && STORE) {
-                // column-strip mode: my last column (block jmax) goes to the GPU on the right (P2P store)
-                const int he = (rsel == 0) ? h0 : (rsel == 1) ? h1 : (rsel == 2) ? h2 : h3;
-                st_cg_int_if(rout + q, he >> 4, (rout != nullptr && j == jmax) ? 1 : 0);
-            }
             if (STORE) {
                 // stage the packed block of this row for the writers
                 if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
@@ -354,20 +398,12 @@ struct Strip {
         }
         // ---------------- scores of the next step ----------------
         scores(next_word);
+        if (EDGE) head_fix(j + 1);
 
         // ---------------- the row above, for the next step ----------------
-        // (Tried: after a miss, also wait for the block after it so that the strip runs one
-        // step behind its producer and the early load always hits.  Misses became rare but the
-        // fill got 5% slower -- one more step of lag per strip -- so the plain poll stays.)
-        if (poll) {
-            if (__builtin_expect((v.x & 3) != wnt, 0)) {
-                int spins = 0;
-                do {
-                    if (++spins > 64) __nanosleep(20);
-                    v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
-                } while ((v.x & 3) != wnt);
-            }
-        }
+        // (v is valid by construction: compute_strip waited for the last block of this run of steps.  A tag
+        // check with a spin loop HERE costs ~80 clk per step even when it never spins: the branch cuts the
+        // group into basic blocks and ptxas can no longer overlap the tail of one step with the head of the next.)
         const bool l0 = (lane == 0);
         A0 = l0 ? (v.x & ~15) : n0;
         A1 = l0 ? v.y : n1;
@@ -400,8 +436,10 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
     }
     trace_stamp(p, strip, 1, lane);
     S.scores(cur[0]);
+    S.head_fix(-lane);
 
     const int gtail = (p.jmax - 8) >> 3;          // groups g <= gtail: t+1 <= jmax for all their steps
+    int known_drained = 0, known_consumed = 0;
 #ifdef SWB_X_GROUPTRACE
     long long dbg_pre = 0, dbg_steps = 0, dbg_post = 0, dbg_n = 0, dbg_e_steps = 0, dbg_e_other = 0;
 #endif
@@ -415,12 +453,23 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         const long long gc0 = clock64();
 #endif
         // ---- staging ring space: the writers must have drained the slots this group overwrites
-        if (STORE && g > stage_slack(KT)) {
+        //      (the flags only grow: the last values read are kept as credits, so a strip whose writers and
+        //      consumer keep up reads them once every few groups instead of three times per group)
+        if (STORE && g - stage_slack(KT) > known_drained) {
+            int d;
+            do {
+                d = lds_volatile_int(drained);
 #pragma unroll
-            for (int k = 0; k < kWriters; ++k) spin_until_ge(drained + 4u * k, g - stage_slack(KT));
+                for (int k = 1; k < kWriters; ++k) d = min(d, lds_volatile_int(drained + 4u * k));
+            } while (d < g - stage_slack(KT));
+            known_drained = d;
         }
         // ---- hand-off ring space (blocks up to t0+7-31 are written in this group)
-        if (ring_consumer && t0 - 80 > 0) spin_until_ge(consumed_out, t0 - 80);
+        if (ring_consumer && t0 - 80 > known_consumed) {
+            int c;
+            do { c = lds_volatile_int(consumed_out); } while (c < t0 - 80);
+            known_consumed = c;
+        }
         sts_volatile_int_if(consumed_in, t0, S.has_in & (lane == 0 ? 1 : 0));
         // ---- sequence words of the next group
 #pragma unroll
@@ -441,23 +490,26 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 #ifdef SWB_X_GROUPTRACE
         const long long gc1 = clock64();
 #endif
-        // Score only: nothing throttles the strips (the writers' back-pressure does that in the full
-        // fill), so every strip would run flush against its producer and pay a failed early poll plus
-        // a spin loop in every step.  Waiting once per group for the LAST block this group needs
-        // keeps all eight polls on the fast path.
-        if (!STORE && S.has_in && t0 + 8 <= p.jmax) {
-            int x = lds_volatile_int4<0>(in_w).x;
-            while ((x & 3) != want_w) x = lds_volatile_int4<0>(in_w).x;
+        // The strip above is polled once per run of kWaitSteps steps, for the LAST block the run needs (the
+        // producer publishes its blocks in order); inside a run there is no branch.  This costs kWaitSteps
+        // steps of extra lag behind the producer and saves a third of every step.
+#define SWB_WAIT(H)                                                                                       \
+        if (S.has_in) {                                                                                   \
+            const int xb = min(t0 + kWaitSteps * ((H) + 1), p.jmax);                                      \
+            if (xb > t0 + kWaitSteps * (H)) wait_block(S.ring_in, xb);                                    \
         }
 #define SWB_STEP(E, I) S.template step<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w)
         if (g >= 4 && g <= gtail) {
-            SWB_STEP(false, 0); SWB_STEP(false, 1); SWB_STEP(false, 2); SWB_STEP(false, 3);
+            SWB_WAIT(0) SWB_STEP(false, 0); SWB_STEP(false, 1); SWB_STEP(false, 2); SWB_STEP(false, 3);
+            if (kWaitSteps == 4) { SWB_WAIT(1) }
             SWB_STEP(false, 4); SWB_STEP(false, 5); SWB_STEP(false, 6); SWB_STEP(false, 7);
         } else {
-            SWB_STEP(true, 0); SWB_STEP(true, 1); SWB_STEP(true, 2); SWB_STEP(true, 3);
+            SWB_WAIT(0) SWB_STEP(true, 0); SWB_STEP(true, 1); SWB_STEP(true, 2); SWB_STEP(true, 3);
+            if (kWaitSteps == 4) { SWB_WAIT(1) }
             SWB_STEP(true, 4); SWB_STEP(true, 5); SWB_STEP(true, 6); SWB_STEP(true, 7);
         }
 #undef SWB_STEP
+#undef SWB_WAIT
 #ifdef SWB_X_GROUPTRACE
         const long long gc2 = clock64();
 #endif
@@ -480,15 +532,6 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
     }
     return;
 #endif
-    if (STORE && p.right_flags != nullptr) {
-        // every lane's boundary stores are ordered before the flag (system scope: another GPU reads them)
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) {
-            int* f = p.right_flags + (strip % p.nstrips);
-            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(p.epoch) : "memory");
-        }
-    }
     trace_stamp(p, strip, 4, lane);
 }
 
@@ -546,7 +589,11 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #endif
         const int v = 32 * r + lane;
         // (the valid rows of a strip are its first nvalid ones: the last strip of a pair may be partial)
-        const bool interior = (32 * r - Emax >= (p.left_in != nullptr ? 1 : 0)) && (32 * r + 31 - Emin <= m);
+        const bool interior = (32 * r - Emax >= (p.left_in != nullptr ? 1 : 0)) && (32 * r + 31 - Emin <= m - (p.right_out != nullptr ? 1 : 0));
+#ifdef SWB_X_NOWRITER
+        if (interior && nvalid == 32) {
+        } else
+#endif
         if (interior && nvalid == 32) {
             // batches of 8 rows: all table and data loads first, then the 16 stores
 #pragma unroll 1
@@ -594,6 +641,9 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                     // hand-off marker that ends this GPU's part of the backtrack
                     __stcs(hp + pdelta, (c == 0 && p.left_in != nullptr) ? kHandOff : (k & 3));
                     if (c > 0 || p.left_in == nullptr) mx = max(mx, k);
+                    // ... and my last column is the boundary column of the GPU on the right (P2P store over NVLink)
+                    if (c == m && p.right_out != nullptr)
+                        asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.right_out + r0 + 32 * sub + l), "r"(k >> 4) : "memory");
                 }
             }
         }
@@ -607,6 +657,13 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #ifdef SWB_X_WRITERTRACE
     if (p.trace && lane == 0 && sub == 0) { p.trace[strip * 8 + 5] = dw_wait; p.trace[strip * 8 + 6] = dw_work; p.trace[strip * 8 + 7] = dw_n; }
 #endif
+    if (p.right_flags != nullptr && nvalid > 0) {
+        // column-strip mode: every lane's boundary stores are ordered before the flag the right GPU polls
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0)
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p.right_flags + (r0 - 1) / 32 + sub), "r"(p.epoch) : "memory");
+    }
     // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel)
     const int hm = __reduce_max_sync(0xffffffffu, mx) >> 4;
     if (lane == 0 && hm > 0) {
@@ -631,13 +688,15 @@ __device__ __forceinline__ void loader_band(const int4* src, const int nblocks, 
         const int limit = min(nblocks, *consumed + kRing);
         const int j = base + lane;
         bool ok = false;
+        int4 v = make_int4(0, 0, 0, 0);
         if (j < limit) {
-            const int4 v = ld_cg_int4(src + j);
+            v = ld_cg_int4(src + j);
             ok = (v.x & 3) == 1 + (((j + 32) >> 6) & 1);
-            if (ok) sts_volatile_int4(ring + ((j + 32) & (kRing - 1)), v);
         }
         const unsigned mask = __ballot_sync(0xffffffffu, ok);
         const int lead = (mask == 0xffffffffu) ? 32 : (__ffs(~mask) - 1);
+        // blocks enter the ring in order (the consumer polls only the last block of a run of steps)
+        if (lane < lead) sts_volatile_int4(ring + ((j + 32) & (kRing - 1)), v);
         base += lead;
         if (lead == 0) { if (++idle > 2) __nanosleep(idle > 64 ? 400 : 60); } else idle = 0;
     }
@@ -729,7 +788,7 @@ fill_kernel(const FillParams p_in)
         // keep the scoring constants in registers: a shuffle result is opaque to ptxas, which
         // otherwise re-reads them from the constant bank at the head of every step, on the
         // dependency chain
-        S.sm = opaque(p.s_match); S.sx = opaque(p.s_mismatch); S.gu = opaque(p.g_up); S.gl = opaque(p.g_left);
+        S.sm = opaque(p.s_match); S.sx = opaque(p.s_mismatch); S.gu = opaque(p.g_up); S.gl = opaque(p.g_left); S.g16 = opaque(p.g_left - kTieLeft);
         S.A0 = S.A1 = S.A2 = S.A3 = 0; S.dgp = 0;
         S.sa_base = (unsigned)__cvta_generic_to_shared(stage4 + ((size_t)w * kStripRows + (size_t)kR * lane) * KT);
         S.sa = S.sa_base + 16u * (unsigned)lane;                 // slot (t + lane) & (KT-1) at t = 0
@@ -737,26 +796,32 @@ fill_kernel(const FillParams p_in)
         S.ring_out = (unsigned)__cvta_generic_to_shared(rings + (size_t)(w + 1 < wpc ? w + 1 : w) * kRing);
         S.jmax = p.jmax;
         S.mcols = (int)p.m;
-        S.rsel = (int)(p.m & 3);
-        S.rout = (STORE && p.right_out != nullptr) ? p.right_out + r0 + kR * lane : nullptr;
-        if (STORE && p.left_in != nullptr) {
-            // column-strip mode: the 64 boundary values of this strip come from the GPU on the left
-            const int* f = p.left_flags + (r0 - 1) / kStripRows;
-            int v;
-            do {
-                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                if (v != p.epoch) __nanosleep(200);
-            } while (v != p.epoch);
+        {
+            const int g16 = p.g_left - kTieLeft;                 // 16 * gap
+            if (STORE && p.left_in != nullptr) {
+                // column-strip mode: the boundary values of this strip come from the GPU on the left, whose
+                // writer warps publish them in pieces of 32 rows
 #pragma unroll
-            for (int q = 0; q < kR; ++q) {
-                const long long row = r0 + kR * lane + q;
-                int hv = 0;
-                if (row <= p.n) asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(hv) : "l"(p.left_in + row) : "memory");
-                S.lbk[q] = 16 * hv;
+                for (int k = 0; k < kWriters; ++k) {
+                    if (r0 + 32 * k > p.n) break;
+                    const int* f = p.left_flags + (r0 - 1) / 32 + k;
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                        if (v != p.epoch) __nanosleep(200);
+                    } while (v != p.epoch);
+                }
+#pragma unroll
+                for (int q = 0; q < kR; ++q) {
+                    const long long row = r0 + kR * lane + q;
+                    int hv = 0;
+                    if (row <= p.n) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(hv) : "l"(p.left_in + row) : "memory");
+                    S.lb[q] = 16 * hv - g16;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < kR; ++q) S.lb[q] = -g16;
             }
-        } else {
-#pragma unroll
-            for (int q = 0; q < kR; ++q) S.lbk[q] = kTieNone;
         }
         S.has_in = opaque(r0 > 1 ? 1 : 0);
         const bool next_row = (r0 + kStripRows <= p.n);          // a strip below exists
