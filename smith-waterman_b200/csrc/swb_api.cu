@@ -132,6 +132,7 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
     if (store && (!dH || !dP || pitch < m + 1)) return SWB_ERR_ARG;
     if (store && npairs > 1 && pair_stride < (n + 1) * pitch) return SWB_ERR_ARG;
     if (m >= (1LL << 30) || n >= (1LL << 30)) return SWB_ERR_RANGE;
+    if (store && pitch >= (1LL << 23)) return SWB_ERR_RANGE;      // the writers address a strip with 32-bit byte offsets (64 rows * pitch * 4)
     if (store && ((reinterpret_cast<uintptr_t>(dH) & 15) || (reinterpret_cast<uintptr_t>(dP) & 15))) return SWB_ERR_ALIGN;
     const swb_scoring sc = scoring ? *scoring : kDefaultScoring;
     if (int rc = check_scoring(sc, m, n)) return rc;
@@ -155,7 +156,7 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
     // ---- workspace (stream ordered)
     Workspace ws;
     ws.a4_words = swb::kAPad + (long long)ngroups * swb::kGroup + 16;
-    ws.bstride = (long long)ngroups * swb::kGroup;
+    ws.bstride = (long long)ngroups * swb::kGroup + swb::kBoundaryPad;
     const bool a_on_dev = is_device_ptr(a), b_on_dev = is_device_ptr(b);
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -197,9 +198,11 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
         }
         // band-boundary rows carry their validity tag in the data: clear the tags
         if (boundary_bytes) SWB_CUDA(cudaMemsetAsync(ws.boundary, 0, boundary_bytes, st));
+        SWB_CUDA(cudaMemsetAsync(ws.ticket, 0, 256, st));            // ticket, NUL flag
         const int prep_blocks = (int)std::min<int64_t>((ws.a4_words * npairs + 255) / 256, 1184);
         swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, npairs, ws.a4, ws.a4_words, ws.ticket, ws.gmax, ws.key,
-                                                      ws.strip_max, (long long)(strips * npairs));
+                                                      ws.strip_max, (long long)(strips * npairs), b_d, (long long)(n * npairs),
+                                                      ws.ticket + 1);
         SWB_CUDA(cudaGetLastError());
 
         swb::FillParams p{};
@@ -211,7 +214,7 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
         p.g_left = 16 * sc.gap + swb::kTieLeft;
         p.ngroups = ngroups; p.jmax = jmax; p.wpc = wpc;
         p.boundary = ws.boundary; p.bstride = ws.bstride;
-        p.ticket = ws.ticket; p.strip_max = ws.strip_max; p.gmax = ws.gmax;
+        p.ticket = ws.ticket; p.nul_flag = ws.ticket + 1; p.strip_max = ws.strip_max; p.gmax = ws.gmax;
         p.trace = tuning ? reinterpret_cast<unsigned long long*>(tuning->trace) : nullptr;
         p.nbands = nbands; p.nstrips = strips; p.a4_stride = ws.a4_words; p.pair_stride = pair_stride;
         p.row_best = ws.row_best;

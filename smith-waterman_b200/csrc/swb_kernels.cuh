@@ -54,7 +54,11 @@ namespace swb {
 #endif
 constexpr int kR        = SWB_ROWS_PER_LANE;   // adjacent rows per lane
 constexpr int kStripRows = 32 * kR;    // rows per strip (compute warp)
-constexpr int kWriters  = kR;          // writer warps per strip, 32 rows each
+#ifndef SWB_WRITER_ROWS
+#define SWB_WRITER_ROWS 32
+#endif
+constexpr int kWRows    = SWB_WRITER_ROWS;         // rows of a strip drained by one writer warp (8, 16 or 32)
+constexpr int kWriters  = kStripRows / kWRows;     // writer warps per strip
 // KT (template parameter of the fill kernel) = staging ring depth in steps (16-byte slots per
 // row): 64 for single large pairs, 32 for batches of small pairs (more CTAs per SM)
 constexpr int kRing     = 64;          // hand-off ring capacity in blocks (power of two)
@@ -64,6 +68,7 @@ constexpr int kGroup    = 8;           // steps per synchronisation group
 #endif
 constexpr int kWaitSteps = SWB_WAIT_STEPS;   // steps per poll of the strip above (4 or 8)
 constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
+constexpr int kBoundaryPad = 32;       // spare blocks in front of a band-boundary row (blocks -31..-1 of a strip's first steps)
 constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: compute warps on schedulers 0..wpc-1,
                                        // writers + loader on the others
 constexpr int kDrainRounds = 2;        // writer rounds after the last compute group
@@ -89,9 +94,10 @@ struct FillParams {
     int             ngroups;               // compute groups per strip
     int             jmax;                  // last block holding a valid column: m >> 2
     int             wpc;                   // compute warps (strips) per band
-    int4*           boundary;              // [nbands][bstride] tagged blocks: last row of band k
+    int4*           boundary;              // [nbands][bstride] tagged blocks: last row of band k (kBoundaryPad spare blocks first)
     long long       bstride;
     int*            ticket;                // band ticket counter
+    const int*      nul_flag;              // != 0: b holds a NUL byte (it would match the zero padding of a: see prep_kernel)
     int*            strip_max;             // [nstrips] max H of each strip (atomicMax by its writers)
     int*            gmax;                  // global max H
     unsigned long long* trace;             // optional [nstrips][8] globaltimer stamps (developer tool) or nullptr
@@ -105,7 +111,7 @@ struct FillParams {
     // column-strip mode (one GPU of several working on one pair): this GPU owns columns c0+1..c0+m of
     // the pair; local column 0 is the last column of the GPU to the left.
     const int32_t*  left_in;               // [n+1] H of that column (written by the left GPU), or nullptr
-    const int*      left_flags;            // [ceil(n/32)] == epoch once rows 32k+1..32k+32 are in left_in
+    const int*      left_flags;            // [ceil(n/kWRows)] == epoch once rows kWRows*k+1 .. kWRows*(k+1) are in left_in
     int32_t*        right_out;             // PEER pointer: the right GPU's left_in, or nullptr
     int*            right_flags;           // PEER pointer: the right GPU's left_flags
     int             epoch;
@@ -205,6 +211,12 @@ __device__ __forceinline__ void wait_block(unsigned ring_in, int x)
         v = lds_volatile_int(a);
     }
 }
+__device__ __forceinline__ unsigned long long mad_wide(unsigned a, unsigned b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
 // a value the compiler / ptxas cannot rematerialise from the constant bank
 __device__ __forceinline__ int opaque(int x) { return __shfl_sync(0xffffffffu, x, 0); }
 
@@ -216,7 +228,8 @@ __device__ __forceinline__ int opaque(int x) { return __shfl_sync(0xffffffffu, x
 __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m, long long npairs,
                             unsigned* __restrict__ a4, long long nwords,
                             int* ticket, int* gmax, unsigned long long* key,
-                            int* strip_max, long long nstrips_total)
+                            int* strip_max, long long nstrips_total,
+                            const unsigned char* __restrict__ b, long long nb, int* nul_flag)
 {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
@@ -233,6 +246,15 @@ __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m, lo
         }
         a4[x] = word;
     }
+    // The padding of a is the byte 0.  Unless b holds a NUL byte (never, for the reference's C strings) a padded
+    // position matches nothing, and then -- with mismatch <= 0 and gap < 0 -- column 0, the blocks in front of it
+    // (lanes that have not started yet) and the columns past m evaluate to H = 0 / values below their valid
+    // neighbours by themselves: the compute warp runs the same code on every step of a strip.
+    {
+        bool nul = false;
+        for (long long k = tid; k < nb; k += nth) nul |= (b[k] == 0);
+        if (nul) *nul_flag = 1;
+    }
     for (long long k = tid; k < nstrips_total; k += nth) strip_max[k] = 0;
     for (long long k = tid; k < npairs; k += nth) { gmax[k] = 0; key[k] = ~0ull; }
     if (tid == 0) *ticket = 0;
@@ -246,6 +268,7 @@ struct Strip {
     static constexpr int kRowInts = 4 * KT;
     int lane;
     unsigned b4[kR];              // my rows' characters, replicated in the four bytes
+    unsigned inv[kR];             // 0, or 0x01010101 for a row past n (partial last strip): such a row never matches
     int sm, sx, gu, gl, g16;
     // dependency state (registers): block of the row above my first row for this step, its
     // last element of the previous step (diagonal of my first column), the last cell of
@@ -264,6 +287,8 @@ struct Strip {
     int   lb[kR];                 // 16*(H - gap) of my rows' local column 0 (column-strip mode: H of the left GPU's
                                   // last column; otherwise 16*(0 - gap)): injected as the left neighbour of block 0
     int   rmax[kR], rcol[kR];     // score-only: best clean 16*H of each of my rows and its first column
+    int   kmax;                   // full fill: largest key of my cells in columns 1..m (strip maximum; the writers have no
+                                  // ALU slots to spare for it)
 
     __device__ __forceinline__ void scores(const unsigned aword)
     {
@@ -272,7 +297,7 @@ struct Strip {
 #endif
 #pragma unroll
         for (int q = 0; q < kR; ++q) {
-            const unsigned x = aword ^ b4[q];
+            const unsigned x = (aword ^ b4[q]) | inv[q];
             s[q][0] = (x & 0x000000ffu) ? sx : sm;       // omp_smithW.c:394-399
             s[q][1] = (x & 0x0000ff00u) ? sx : sm;
             s[q][2] = (x & 0x00ff0000u) ? sx : sm;
@@ -284,31 +309,35 @@ struct Strip {
     // and column 0 (first cell of block 0) is the boundary column.  Nothing is forced on the dependency
     // chain: with all inputs zero and the substitution score forced to kSNeg a cell evaluates to
     // NONE / 0 by itself, and the boundary value of column 0 enters as the left neighbour.
-    __device__ __forceinline__ void head_fix(const int jn)
+    __device__ __forceinline__ void head_fix(const unsigned aword, const int jn)
     {
+        // (overrides scores(): two selects per step instead of one per cell)
+        const int sm0 = (jn <= 0) ? kSNeg : sm, sx0 = (jn <= 0) ? kSNeg : sx;
+        const int sm1 = (jn < 0) ? kSNeg : sm, sx1 = (jn < 0) ? kSNeg : sx;
 #pragma unroll
         for (int q = 0; q < kR; ++q) {
-            s[q][0] = (jn <= 0) ? kSNeg : s[q][0];
-            s[q][1] = (jn < 0) ? kSNeg : s[q][1];
-            s[q][2] = (jn < 0) ? kSNeg : s[q][2];
-            s[q][3] = (jn < 0) ? kSNeg : s[q][3];
+            const unsigned x = (aword ^ b4[q]) | inv[q];
+            s[q][0] = (x & 0x000000ffu) ? sx0 : sm0;
+            s[q][1] = (x & 0x0000ff00u) ? sx1 : sm1;
+            s[q][2] = (x & 0x00ff0000u) ? sx1 : sm1;
+            s[q][3] = (x & 0xff000000u) ? sx1 : sm1;
             hl[q] = (jn == 0) ? lb[q] : hl[q];
         }
     }
 
-    // one step.  EDGE: handles the zero column / not-yet-started lanes (first 4 groups) and
-    // the end of the producer's row (last groups).  I = step index inside the group
+    // one step.  MODE 0: interior; bit 0: head of a strip (first 4 groups: the zero column, lanes that have not
+    // started yet); bit 1: tail (last groups: the end of the producer's row, columns past m); 3: both (tiny matrices).  I = step index inside the group
     // (compile time: ring slots and the global hand-off are immediate offsets).
     // next_word: packed characters of the NEXT step (its scores are computed in the shadow
     // of the shuffles).  in_g / out_g: ring addresses of this group's first entries.
-    template <bool EDGE, int I>
+    template <int MODE, int I>
     __device__ __forceinline__ void step(const int t, const unsigned next_word,
                                          const unsigned in_g, const unsigned in_w, const int want, const int want_w,
                                          const unsigned out_g, const unsigned out_w, const int otag, const int otag_w)
     {
         constexpr bool LAST = (I == kGroup - 1);
         const int j = t - lane;
-        const bool poll = has_in && (!EDGE || t + 1 <= jmax);
+        const bool poll = has_in && (!(MODE & 2) || t + 1 <= jmax);
         // block t+1 of the strip above (the row above lane 0's first row in the next step):
         // first try early, it is needed only after the shuffles
         int4 v = make_int4(0, 0, 0, 0);
@@ -361,6 +390,16 @@ struct Strip {
 #endif
             hl[q] = h3;
             if (STORE) {
+                int e0 = k0, e1 = k1, e2 = k2, e3 = k3;
+                if (MODE & 1) e0 = (j == 0) ? 0 : k0;        // column 0 (blocks j < 0 hold NONE)
+                if (MODE & 2) {
+                    const int c = 4 * j;
+                    e0 = (c <= mcols) ? e0 : 0;
+                    e1 = (c + 1 <= mcols) ? k1 : 0;
+                    e2 = (c + 2 <= mcols) ? k2 : 0;
+                    e3 = (c + 3 <= mcols) ? k3 : 0;
+                }
+                kmax = __vimax3_s32(__vimax3_s32(kmax, e0, e1), e2, e3);
                 // stage the packed block of this row for the writers
                 if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
                 if (q == 1) sts_int4<kRowInts * 4>(sa, k0, k1, k2, k3);
@@ -371,7 +410,7 @@ struct Strip {
                 // (strict '>' keeps the earliest column, i.e. the earliest anti-diagonal of the row);
                 // branch-free -- the compute warp must not diverge
                 int v0 = h0, v1 = h1, v2 = h2, v3 = h3;
-                if (EDGE) {
+                if (MODE != 0) {
                     const int c = 4 * j;
                     v0 = (c >= 1 && c <= mcols) ? h0 : -1;
                     v1 = (c + 1 >= 1 && c + 1 <= mcols) ? h1 : -1;
@@ -390,15 +429,16 @@ struct Strip {
 
         // ---------------- hand my last row to the next strip (lane 31 only) ----------------
         {
-            const int started = (!EDGE || j >= 0) ? 1 : 0;
+            const int started = 1;   // (blocks j < 0 go out as well: wrong-epoch ring entries / the spare blocks of the boundary row)
+            (void)j;
             const int4 o = make_int4(u0 | (LAST ? otag_w : otag), u1, u2, u3);
             if (LAST) sts_volatile_int4_if<0>(out_w, o, out_ring & started);
             else      sts_volatile_int4_if<16 * I>(out_g, o, out_ring & started);
             st_cg_int4_if<16 * I>(gout, o, out_glob & started);
         }
         // ---------------- scores of the next step ----------------
-        scores(next_word);
-        if (EDGE) head_fix(j + 1);
+        if (MODE & 1) head_fix(next_word, j + 1);
+        else          scores(next_word);
 
         // ---------------- the row above, for the next step ----------------
         // (v is valid by construction: compute_strip waited for the last block of this run of steps.  A tag
@@ -435,8 +475,9 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         if (lane == 0) { S.A0 = v.x & ~15; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w; }
     }
     trace_stamp(p, strip, 1, lane);
-    S.scores(cur[0]);
-    S.head_fix(-lane);
+    const bool forced = (STORE && p.left_in != nullptr) || opaque(*p.nul_flag) != 0;
+    if (forced) S.head_fix(cur[0], -lane);
+    else        S.scores(cur[0]);
 
     const int gtail = (p.jmax - 8) >> 3;          // groups g <= gtail: t+1 <= jmax for all their steps
     int known_drained = 0, known_consumed = 0;
@@ -499,15 +540,17 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
             if (xb > t0 + kWaitSteps * (H)) wait_block(S.ring_in, xb);                                    \
         }
 #define SWB_STEP(E, I) S.template step<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w)
-        if (g >= 4 && g <= gtail) {
-            SWB_WAIT(0) SWB_STEP(false, 0); SWB_STEP(false, 1); SWB_STEP(false, 2); SWB_STEP(false, 3);
-            if (kWaitSteps == 4) { SWB_WAIT(1) }
-            SWB_STEP(false, 4); SWB_STEP(false, 5); SWB_STEP(false, 6); SWB_STEP(false, 7);
-        } else {
-            SWB_WAIT(0) SWB_STEP(true, 0); SWB_STEP(true, 1); SWB_STEP(true, 2); SWB_STEP(true, 3);
-            if (kWaitSteps == 4) { SWB_WAIT(1) }
-            SWB_STEP(true, 4); SWB_STEP(true, 5); SWB_STEP(true, 6); SWB_STEP(true, 7);
-        }
+        // forced = b holds a NUL byte, or column-strip mode (boundary injection): head and tail steps differ.
+        // Otherwise a full fill runs the interior step everywhere; score only still masks the columns past m.
+#define SWB_GROUP(M) { SWB_WAIT(0) SWB_STEP(M, 0); SWB_STEP(M, 1); SWB_STEP(M, 2); SWB_STEP(M, 3);  \
+                       if (kWaitSteps == 4) { SWB_WAIT(1) }                                          \
+                       SWB_STEP(M, 4); SWB_STEP(M, 5); SWB_STEP(M, 6); SWB_STEP(M, 7); }
+        const bool head = forced && g < 4, tail = (forced || !STORE) && g > gtail;
+        if (!head && !tail) SWB_GROUP(0)
+        else if (head && !tail) SWB_GROUP(1)
+        else if (tail && !head) SWB_GROUP(2)
+        else SWB_GROUP(3)
+#undef SWB_GROUP
 #undef SWB_STEP
 #undef SWB_WAIT
 #ifdef SWB_X_GROUPTRACE
@@ -537,7 +580,7 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 
 // ---------------------------------------------------------------------------------
 // writer warp: drains 32 rows of the staging ring of one strip into H and P
-//   sub = which 32 rows of the strip (0 .. kWriters-1)
+//   sub = which kWRows rows of the strip (0 .. kWriters-1); table entries / row loops use the first kWRows lanes' rows
 // ---------------------------------------------------------------------------------
 template <int KT>
 __device__ __forceinline__ void writer_strip(const FillParams& p, const long long r0, const int sub, const int lane,
@@ -550,24 +593,30 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
     // first element sits on a 128-byte line of H (and P); E is the smallest such offset for
     // which lane cl has finished those columns by the end of compute group r
     constexpr int kRowInts = 4 * KT;
-    const int rho = 32 * sub + lane;
+    const int rho = kWRows * sub + (lane & (kWRows - 1));
     const int cl  = rho / kR;
     const long long row = r0 + rho;
+    const bool myrow = lane < kWRows && row <= p.n;
     const int ph = (int)((row * p.pitch) & 31);
     const int d  = (cl + ((31 - ph) >> 2)) >> 3;
     const int E  = 32 * d + ph;
     const long long G0 = row * p.pitch - E;                      // multiple of 32
     const int F  = (8 * cl - E) & (kRowInts - 1);                // ring index of column c is (c + 8*cl) mod kRowInts
     const unsigned long long hb = (unsigned long long)(p.H + G0);
-    rowtab[lane] = make_int4((int)(unsigned)hb, (int)(unsigned)(hb >> 32), F, E);
-    const unsigned rowmask = __ballot_sync(0xffffffffu, row <= p.n);
+    if (lane < kWRows) rowtab[lane] = make_int4((int)(unsigned)hb, (int)(unsigned)(hb >> 32), F, E);
+    // the same for the fast path: byte offset of the row's segment base from the strip's first row (fits 32 bits:
+    // kStripRows * pitch * 4 < 2^32 is checked by the host) and F
+    int2* rowoff = reinterpret_cast<int2*>(rowtab + 32);
+    const unsigned long long hbase = (unsigned long long)p.H + 4ull * (unsigned long long)(r0 * p.pitch - 1024);     // (E < 1024)
+    if (lane < kWRows) rowoff[lane] = make_int2((int)(unsigned)(4 * (G0 - r0 * p.pitch + 1024)), F);
+    const unsigned one = (unsigned)opaque(1);
+    const unsigned rowmask = __ballot_sync(0xffffffffu, myrow);
     const int nvalid = __popc(rowmask);
-    const int Emax = __reduce_max_sync(0xffffffffu, row <= p.n ? E : 0);
-    const int Emin = __reduce_min_sync(0xffffffffu, row <= p.n ? E : 0x7fffffff);
+    const int Emax = __reduce_max_sync(0xffffffffu, myrow ? E : 0);
+    const int Emin = __reduce_min_sync(0xffffffffu, myrow ? E : 0x7fffffff);
     __syncwarp();
-    const int* mystage = stage + (size_t)32 * sub * kRowInts;
+    const int* mystage = stage + (size_t)kWRows * sub * kRowInts;
 
-    int mx = 0;
     const int rounds = p.ngroups + kDrainRounds;
     const int m = (int)p.m;
     const long long pdelta = (long long)(p.P - p.H);              // P[i] sits pdelta ints after H[i]
@@ -591,29 +640,31 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
         // (the valid rows of a strip are its first nvalid ones: the last strip of a pair may be partial)
         const bool interior = (32 * r - Emax >= (p.left_in != nullptr ? 1 : 0)) && (32 * r + 31 - Emin <= m - (p.right_out != nullptr ? 1 : 0));
 #ifdef SWB_X_NOWRITER
-        if (interior && nvalid == 32) {
+        if (interior && nvalid == kWRows) {
         } else
 #endif
-        if (interior && nvalid == 32) {
-            // batches of 8 rows: all table and data loads first, then the 16 stores
+        if (interior && nvalid == kWRows) {
+            // batches of 8 rows: all table and data loads first, then the 16 stores.  Per row the ALU pipe
+            // sees the ring index (2 ops) and the unpacking (2 ops); the two addresses are one IMAD.WIDE each
+            // (row offset in bytes * 1 + the 64-bit address of this lane's column in the strip's first row)
+            const unsigned long long hcol = hbase + 4ull * (unsigned)v, pcol = hcol + 4ull * (unsigned long long)pdelta;
 #pragma unroll 1
-            for (int l0 = 0; l0 < 32; l0 += 8) {
-                int k[8]; int32_t* hp[8];
+            for (int l0 = 0; l0 < kWRows; l0 += 8) {
+                int k[8]; unsigned off[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int4 tb = rowtab[l0 + i];
-                    hp[i] = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.y << 32) | (unsigned)tb.x) + v;
-                    k[i] = mystage[(l0 + i) * kRowInts + ((v + tb.z) & (kRowInts - 1))];
+                    const int2 tb = rowoff[l0 + i];
+                    off[i] = (unsigned)tb.x;
+                    k[i] = mystage[(l0 + i) * kRowInts + ((v + tb.y) & (kRowInts - 1))];
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
 #ifndef SWB_X_NOSTG
-                    __stcs(hp[i], k[i] >> 4);
-                    __stcs(hp[i] + pdelta, k[i] & 3);
+                    __stcs(reinterpret_cast<int32_t*>(mad_wide(off[i], one, hcol)), k[i] >> 4);
+                    __stcs(reinterpret_cast<int32_t*>(mad_wide(off[i], one, pcol)), k[i] & 3);
 #else
-                    if (k[i] == 0x7ffffff1) __stcs(hp[i], k[i] >> 4);
+                    if (k[i] == 0x7ffffff1) __stcs(reinterpret_cast<int32_t*>(mad_wide(off[i], one, hcol)), k[i] >> 4);
 #endif
-                    mx = max(mx, k[i]);
                 }
             }
         } else if (interior) {
@@ -625,11 +676,10 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                 const int k = mystage[l * kRowInts + ((v + tb.z) & (kRowInts - 1))];
                 __stcs(hp, k >> 4);
                 __stcs(hp + pdelta, k & 3);
-                mx = max(mx, k);
             }
         } else {
 #pragma unroll 2
-            for (int l = 0; l < 32; ++l) {
+            for (int l = 0; l < kWRows; ++l) {
                 const int4 tb = rowtab[l];
                 const int idx = (v + tb.z) & (kRowInts - 1);
                 const int c = v - tb.w;
@@ -640,10 +690,9 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                     // column-strip mode: local column 0 belongs to the GPU on the left; its P holds the
                     // hand-off marker that ends this GPU's part of the backtrack
                     __stcs(hp + pdelta, (c == 0 && p.left_in != nullptr) ? kHandOff : (k & 3));
-                    if (c > 0 || p.left_in == nullptr) mx = max(mx, k);
                     // ... and my last column is the boundary column of the GPU on the right (P2P store over NVLink)
                     if (c == m && p.right_out != nullptr)
-                        asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.right_out + r0 + 32 * sub + l), "r"(k >> 4) : "memory");
+                        asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.right_out + r0 + kWRows * sub + l), "r"(k >> 4) : "memory");
                 }
             }
         }
@@ -662,13 +711,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
         __threadfence_system();
         __syncwarp();
         if (lane == 0)
-            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p.right_flags + (r0 - 1) / 32 + sub), "r"(p.epoch) : "memory");
-    }
-    // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel)
-    const int hm = __reduce_max_sync(0xffffffffu, mx) >> 4;
-    if (lane == 0 && hm > 0) {
-        atomicMax(p.strip_max + strip, hm);
-        atomicMax(p.gmax, hm);
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p.right_flags + (r0 - 1) / kWRows + sub), "r"(p.epoch) : "memory");
     }
 #if !defined(SWB_X_GROUPTRACE) && !defined(SWB_X_WRITERTRACE)
     trace_stamp(p, strip, 5 + (sub & 1), lane);
@@ -710,7 +753,7 @@ __host__ __device__ constexpr int fill_block_threads(int wpc, bool store)
 }
 __host__ __device__ constexpr size_t fill_smem_bytes(int wpc, int KT, bool store)
 {
-    return (size_t)wpc * ((store ? (size_t)kStripRows * 4 * KT * sizeof(int) + kWriters * 32 * sizeof(int4) : 0) +
+    return (size_t)wpc * ((store ? (size_t)kStripRows * 4 * KT * sizeof(int) + kWriters * 48 * sizeof(int4) : 0) +
                           kRing * sizeof(int4));
 }
 
@@ -721,7 +764,7 @@ __host__ __device__ constexpr size_t fill_smem_bytes(int wpc, int KT, bool store
 // STORE = false is the score-only variant: no staging, no writers, per-row best cells instead.
 // ---------------------------------------------------------------------------------
 template <int KT, bool STORE>
-__global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true))
+__global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true), (KT == 64 && STORE) ? 1 : 2)
 fill_kernel(const FillParams p_in)
 {
     extern __shared__ __align__(1024) int4 smem4[];
@@ -756,7 +799,7 @@ fill_kernel(const FillParams p_in)
 
     int4* stage4  = smem4;                                       // [wpc][kStripRows][KT]   (STORE only)
     int4* rings   = stage4 + (STORE ? (size_t)wpc * kStripRows * KT : 0);   // [wpc][kRing]
-    int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc*kWriters][32]      (STORE only)
+    int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc*kWriters][48]      (STORE only)
 
     for (int i = threadIdx.x; i < wpc * kRing; i += blockDim.x) rings[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
@@ -783,7 +826,8 @@ fill_kernel(const FillParams p_in)
         for (int q = 0; q < kR; ++q) {
             const long long row = r0 + kR * lane + q;
             S.b4[q] = (row <= p.n) ? (unsigned)p.b[row - 1] * 0x01010101u : 0u;
-            S.hl[q] = 0; S.rmax[q] = 0; S.rcol[q] = 0;
+            S.inv[q] = (row <= p.n) ? 0u : 0x01010101u;
+            S.hl[q] = 0; S.rmax[q] = 0; S.rcol[q] = 0; S.kmax = 0;
         }
         // keep the scoring constants in registers: a shuffle result is opaque to ptxas, which
         // otherwise re-reads them from the constant bank at the head of every step, on the
@@ -803,8 +847,8 @@ fill_kernel(const FillParams p_in)
                 // writer warps publish them in pieces of 32 rows
 #pragma unroll
                 for (int k = 0; k < kWriters; ++k) {
-                    if (r0 + 32 * k > p.n) break;
-                    const int* f = p.left_flags + (r0 - 1) / 32 + k;
+                    if (r0 + kWRows * k > p.n) break;
+                    const int* f = p.left_flags + (r0 - 1) / kWRows + k;
                     int v;
                     do {
                         asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
@@ -830,13 +874,19 @@ fill_kernel(const FillParams p_in)
         S.out_glob = (next_row && (w + 1 == wpc) && lane == 31) ? 1 : 0;
         // block j = t - lane of step t goes to gout[j]: base of the group's first step, the
         // step index is an immediate (only lane 31's copy is ever dereferenced, from t = 31 on)
-        S.gout = p.boundary + (size_t)(next_row && (w + 1 == wpc) ? band : 0) * p.bstride - lane;
+        S.gout = p.boundary + (size_t)(next_row && (w + 1 == wpc) ? band : 0) * p.bstride + kBoundaryPad - lane;
         const unsigned* aw = p.a4 + kAPad - lane;                // aw[t] = characters of block t - lane
         const long long strip = (r0 - 1) / kStripRows;
         compute_strip<KT, STORE>(p, S, aw, (unsigned)__cvta_generic_to_shared(s_staged + w),
                       (unsigned)__cvta_generic_to_shared(s_drained + w * kWriters),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, strip + pair * p.nstrips);
+        if (STORE) {
+            // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel).  The rows past n of a
+            // partial strip never match (inv), so their cells stay below the cells above them.
+            const int mx = __reduce_max_sync(0xffffffffu, S.kmax) >> 4;
+            if (lane == 0 && mx > 0) { atomicMax(p.strip_max + strip, mx); atomicMax(p.gmax, mx); }
+        }
         if (!STORE) {
             // per-row best cells and the strip / global maxima (maxPos is reduced from them)
             int mx = 0;
@@ -857,12 +907,12 @@ fill_kernel(const FillParams p_in)
         const long long r0 = band_r0 + (long long)kStripRows * cw;
         if (r0 > p.n) return;                                    // (a writer without valid rows still runs: it owns a drained flag)
         writer_strip<KT>(p, r0, sub, lane, reinterpret_cast<const int*>(stage4 + (size_t)cw * kStripRows * KT),
-                     rowtabs + (size_t)wi * 32, s_staged + cw, s_drained + wi,
+                     rowtabs + (size_t)wi * 48, s_staged + cw, s_drained + wi,
                      (r0 - 1) / kStripRows);
     } else if (role == 2) {
         // ------------------------------------------------ loader
         if (band == 0 || band_r0 > p.n) return;
-        loader_band(p.boundary + (size_t)(band - 1) * p.bstride, p.jmax + 1, rings, lane, s_consumed);
+        loader_band(p.boundary + (size_t)(band - 1) * p.bstride + kBoundaryPad, p.jmax + 1, rings, lane, s_consumed);
     }
 }
 
