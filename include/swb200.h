@@ -146,6 +146,48 @@ int swb_fill_batch_async(const char* a, int64_t m, const char* b, int64_t n, int
                          const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch, int64_t pair_stride,
                          int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream, const swb_tuning* tuning);
 
+/* ---- column-strip mode: ONE pair across several GPUs (BASELINE config "100000x100000 single pair,
+ * column-strip wavefront pipelined across 2/4/8 B200 with NVLink P2P boundary exchange").
+ * The reference has no multi-GPU form; this extends the nDiag wavefront (omp_smithW.c:203-216).
+ * GPU g owns the columns col0+1 .. col0+m_local of every row and holds them as its own row-major
+ * matrices dH/dP of (n+1) x pitch, pitch >= m_local+1; local column j is global column col0+j and
+ * local column 0 is a copy of the last column of the GPU on the left (the zero column for GPU 0).
+ *   left_in     DEVICE int32[n+1] on this GPU: H of that column, written by the left GPU's fill
+ *               kernel with peer stores while it runs (NULL for the first strip)
+ *   left_flags  DEVICE int32[swb_strip_flag_count(n)] on this GPU: flag k == epoch once the rows of
+ *               piece k are in left_in (NULL with left_in)
+ *   right_out / right_flags  the right GPU's left_in / left_flags as PEER pointers valid on this GPU
+ *               (cudaIpcOpenMemHandle / peer access; NULL for the last strip)
+ *   epoch       nonzero, different from the previous call's on the same buffers
+ * The fill kernel of strip g+1 waits on the flags piece by piece, so all strips run concurrently,
+ * each a few row-blocks behind its left neighbour; there is no collective in the data path.
+ * d_maxPos / d_maxScore: the LOCAL maximum over local columns 1..m_local (index i*pitch + j_local,
+ * reference tie-break).  In P, local column 0 of a strip with a left neighbour holds 5 (not a
+ * reference code): the backtrack hand-off marker. */
+int swb_fill_strip_async(const char* a_local, int64_t m_local, const char* b, int64_t n,
+                         const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch,
+                         const int32_t* left_in, const int32_t* left_flags, int32_t* right_out, int32_t* right_flags,
+                         int32_t epoch, int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream,
+                         const swb_tuning* tuning);
+int64_t swb_strip_flag_count(int64_t n);
+
+/* backtrack (omp_smithW.c:405-420) from an arbitrary start cell of a strip: follows P from startPos,
+ * negating the path, until a NONE cell or the hand-off marker of local column 0.  d_endPos (DEVICE
+ * int64) receives the index of the cell that ended the walk: if it lies in local column 0 of a strip
+ * with a left neighbour the path continues at the same row in the last column of that neighbour. */
+int swb_backtrack_from_async(int32_t* dP, int64_t pitch, int64_t startPos, int64_t* d_pathLen, int64_t* d_endPos,
+                             int device, void* stream);
+
+/* Boundary buffers that another process maps (cudaMalloc + CUDA IPC): allocation (zero-filled),
+ * 64-byte IPC handle, mapping a peer's handle on `device`, and peer access between two devices of
+ * one process. */
+void* swb_ipc_alloc(size_t bytes, int device);
+void  swb_ipc_free(void* p, int device);
+int   swb_ipc_get_handle(void* p, unsigned char* out64);
+int   swb_ipc_open(const unsigned char* handle64, int device, void** out);
+int   swb_ipc_close(void* p, int device);
+int   swb_enable_peer(int device, int peer);
+
 /* The reference's generate() (omp_smithW.c:489-519): srand(seed) then m+1 draws
  * for a and n+1 draws for b with this libc's rand(), 0->A 2->C 3->G else T.
  * Host-side helper so that callers get the reference's sequences for a seed. */

@@ -70,6 +70,16 @@ def _load() -> C.CDLL:
     L.swb_score_only_async.argtypes = [vp, i64, vp, i64, i64, C.POINTER(Scoring), vp, vp, C.c_int, vp, C.POINTER(Tuning)]
     L.swb_fill_batch_async.argtypes = [vp, i64, vp, i64, i64, C.POINTER(Scoring), vp, vp, i64, i64, vp, vp, C.c_int, vp,
                                        C.POINTER(Tuning)]
+    L.swb_fill_strip_async.argtypes = [vp, i64, vp, i64, C.POINTER(Scoring), vp, vp, i64, vp, vp, vp, vp, i32, vp, vp,
+                                       C.c_int, vp, C.POINTER(Tuning)]
+    L.swb_strip_flag_count.argtypes = [i64]; L.swb_strip_flag_count.restype = i64
+    L.swb_backtrack_from_async.argtypes = [vp, i64, i64, vp, vp, C.c_int, vp]
+    L.swb_ipc_alloc.argtypes = [C.c_size_t, C.c_int]; L.swb_ipc_alloc.restype = vp
+    L.swb_ipc_free.argtypes = [vp, C.c_int]; L.swb_ipc_free.restype = None
+    L.swb_ipc_get_handle.argtypes = [vp, vp]
+    L.swb_ipc_open.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.swb_ipc_close.argtypes = [vp, C.c_int]
+    L.swb_enable_peer.argtypes = [C.c_int, C.c_int]
     L.swb_generate.argtypes = [C.c_uint, i64, i64, vp, vp]; L.swb_generate.restype = None
     L.swb_timer_create.argtypes = [C.POINTER(vp), C.c_int]; L.swb_timer_create.restype = C.c_int
     L.swb_timer_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]; L.swb_timer_elapsed_ms.restype = C.c_int
@@ -77,7 +87,9 @@ def _load() -> C.CDLL:
     L.swb_host_alloc.argtypes = [C.c_size_t]; L.swb_host_alloc.restype = vp
     L.swb_host_free.argtypes = [vp]; L.swb_host_free.restype = None
     for name in ("swb_fill_async", "swb_fill", "swb_backtrack_async", "swb_backtrack", "swb_align_host",
-                 "swb_ctx_create", "swb_ctx_align", "swb_score_only", "swb_score_only_async", "swb_fill_batch_async"):
+                 "swb_ctx_create", "swb_ctx_align", "swb_score_only", "swb_score_only_async", "swb_fill_batch_async",
+                 "swb_fill_strip_async", "swb_backtrack_from_async", "swb_ipc_get_handle", "swb_ipc_open", "swb_ipc_close",
+                 "swb_enable_peer"):
         getattr(L, name).restype = C.c_int
     return L
 

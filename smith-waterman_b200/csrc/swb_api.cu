@@ -361,6 +361,8 @@ int swb_fill_strip_async(const char* a_local, int64_t m_local, const char* b, in
                      &link);
 }
 
+int64_t swb_strip_flag_count(int64_t n) { return n <= 0 ? 0 : (n + swb::kWRows - 1) / swb::kWRows; }
+
 void* swb_ipc_alloc(size_t bytes, int device)
 {
     DeviceGuard guard(device);
