@@ -18,7 +18,7 @@ t=tr.view(strips,8).cpu().numpy().astype(object)
 print("strip | steady groups: pre-wait/grp  steps/grp (per step)  post/grp | edge groups 0-3: steps per step, other per group")
 for s in list(range(6))+list(range(strips//2,strips//2+4))+[strips-2,strips-1]:
     r=t[s]; n=max(r[5],1)
-    slow=int(r[7])>>32; it=int(r[7])&0xffffffff
-    print(f"{s:4d} | {r[2]/n:8.1f} {r[3]/n:8.1f} ({r[3]/n/8:6.1f}) {r[4]/n:8.1f} | {r[6]/32:7.1f}  slow-path entries {slow} iterations {it} (of {int(n)*8+64} steps)")
+    drain=(int(r[7])>>32)*16; cons=(int(r[7])&0xffffffff)*16
+    print(f"{s:4d} | {r[2]/n:8.1f} {r[3]/n:8.1f} ({r[3]/n/8:6.1f}) {r[4]/n:8.1f} | {r[6]/32:7.1f}  of pre: writers' ring space {drain/n:6.1f}  consumer's ring space {cons/n:6.1f} clk/group")
 n=np.maximum(t[:,5],1)
 print("mean: pre %.1f steps %.1f (%.1f/step) post %.1f | edge %.1f/step" % ((t[:,2]/n).mean(), (t[:,3]/n).mean(), (t[:,3]/n).mean()/8, (t[:,4]/n).mean(), (t[:,6]/32).mean()))
