@@ -495,6 +495,9 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         if (lane == 0) { S.A0 = v.x & ~15; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w; }
     }
     trace_stamp(p, strip, 1, lane);
+#ifdef SWB_X_CLKTRACE
+    const long long clk_gate = clock64();
+#endif
     const bool forced = (STORE && p.left_in != nullptr) || opaque(*p.nul_flag) != 0;
     if (forced) S.head_fix(cur[0], -lane);
     else        S.scores(cur[0]);
@@ -605,6 +608,9 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
     return;
 #endif
     trace_stamp(p, strip, 4, lane);
+#ifdef SWB_X_CLKTRACE
+    if (p.trace && lane == 0) { p.trace[strip * 8 + 6] = clock64() - clk_gate; }
+#endif
 }
 
 // ---------------------------------------------------------------------------------
@@ -714,24 +720,34 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
             // sees the ring index (2 ops) and the unpacking (2 ops); the two addresses are one IMAD.WIDE each
             // (row offset in bytes * 1 + the 64-bit address of this lane's column in the strip's first row)
             const unsigned long long hcol = hbase + 4ull * (unsigned)v, pcol = hcol + 4ull * (unsigned long long)pdelta;
-#pragma unroll 1
-            for (int l0 = 0; l0 < kWRows; l0 += 8) {
-                int k[8]; unsigned off[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int2 tb = rowoff[l0 + i];
-                    off[i] = (unsigned)tb.x;
-                    k[i] = mystage[(l0 + i) * kRowInts + ((v + tb.y) & (kRowInts - 1))];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-#ifndef SWB_X_NOSTG
-                    SWB_ST(reinterpret_cast<int32_t*>(mad_wide(off[i], one, hcol)), k[i] >> 4);
-                    SWB_ST(reinterpret_cast<int32_t*>(mad_wide(off[i], one, pcol)), k[i] & 3);
-#else
-                    if (k[i] == 0x7ffffff1) __stcs(reinterpret_cast<int32_t*>(mad_wide(off[i], one, hcol)), k[i] >> 4);
+#ifndef SWB_WRITER_DEPTH
+#define SWB_WRITER_DEPTH 4
 #endif
+            // rolling pipeline over the rows: the loads of row i+D are issued before the two stores of row i, so the
+            // stores leave the SM as a steady trickle.  (Batches of 8 rows = bursts of 16 STGs: the shuffles and
+            // shared-memory accesses on the compute warps' chain queue behind them in the SM's load/store pipeline.)
+            constexpr int D = SWB_WRITER_DEPTH;
+            int k[D]; unsigned off[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const int2 tb = rowoff[i];
+                off[i] = (unsigned)tb.x;
+                k[i] = mystage[i * kRowInts + ((v + tb.y) & (kRowInts - 1))];
+            }
+#pragma unroll
+            for (int i = 0; i < kWRows; ++i) {
+                const int kk = k[i % D]; const unsigned oo = off[i % D];
+                if (i + D < kWRows) {
+                    const int2 tb = rowoff[i + D];
+                    off[i % D] = (unsigned)tb.x;
+                    k[i % D] = mystage[(i + D) * kRowInts + ((v + tb.y) & (kRowInts - 1))];
                 }
+#ifndef SWB_X_NOSTG
+                SWB_ST(reinterpret_cast<int32_t*>(mad_wide(oo, one, hcol)), kk >> 4);
+                SWB_ST(reinterpret_cast<int32_t*>(mad_wide(oo, one, pcol)), kk & 3);
+#else
+                if (kk == 0x7ffffff1) __stcs(reinterpret_cast<int32_t*>(mad_wide(oo, one, hcol)), kk >> 4);
+#endif
             }
 #endif
         } else if (interior) {
@@ -783,7 +799,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
         if (lane == 0)
             asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p.right_flags + (r0 - 1) / kWRows + sub), "r"(p.epoch) : "memory");
     }
-#if !defined(SWB_X_GROUPTRACE) && !defined(SWB_X_WRITERTRACE)
+#if !defined(SWB_X_GROUPTRACE) && !defined(SWB_X_WRITERTRACE) && !defined(SWB_X_CLKTRACE)
     trace_stamp(p, strip, 5 + (sub & 1), lane);
 #endif
 }
@@ -1143,12 +1159,20 @@ __device__ __forceinline__ void bt_fetch_band(int* buf, const int32_t* P, long l
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     asm volatile("bar.sync 1, %0;" ::"n"(kBtFetchers) : "memory");
-    // marker columns (band columns 0 and 127), over the landed data
-    for (int e = tid; e < 2 * kBtRows; e += kBtFetchers) {
-        const int rr = e >> 1;
-        long long r;
-        const int sh = (int)(bt_row_start(i0, c0, pitch, rr, r) & 3);
-        buf[rr * kBtRS + sh + ((e & 1) ? kBtCols - 1 : 0)] = kBtMark;
+    // A row landed with its first band column at offset (row start & 3): shift every row into place (one warp per
+    // row, in place: all loads of the row precede its stores), so that band column k of band row rr is
+    // buf[rr * kBtRS + k] and the walker moves with constant strides.
+    {
+        const int lane = tid & 31, fw = tid >> 5;
+        for (int rr = fw; rr < kBtRows; rr += kBtFetchers / 32) {
+            long long r;
+            const int sh = (int)(bt_row_start(i0, c0, pitch, rr, r) & 3);
+            int* row = buf + rr * kBtRS;
+            const int v0 = row[sh + 4 * lane], v1 = row[sh + 4 * lane + 1], v2 = row[sh + 4 * lane + 2], v3 = row[sh + 4 * lane + 3];
+            __syncwarp();
+            // marker columns (band columns 0 and 127)
+            *reinterpret_cast<int4*>(row + 4 * lane) = make_int4(lane == 0 ? kBtMark : v0, v1, v2, lane == 31 ? kBtMark : v3);
+        }
     }
 }
 
@@ -1162,7 +1186,7 @@ __device__ __forceinline__ void bt_writeback(const int* buf, const int* list, in
         const int rr = a / kBtRS;
         long long r;
         const long long s = bt_row_start(i0, c0, pitch, rr, r);
-        P[s + (a - rr * kBtRS - (int)(s & 3))] = -buf[a];
+        P[s + (a - rr * kBtRS)] = -buf[a];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kBtFetchers) : "memory");   // all of it read before the buffer is reused
 }
@@ -1189,7 +1213,6 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
     long long bi = i, bc = j;                           // entry cell of the band in buffer `cur`
     long long pbi = 0, pbc = 0;                         // entry cell of the previous band (buffer cur^1) to write back
     bool have_prev = false;
-    const int nu = (int)((pitch + 1) & 3);              // the row shift goes down by nu (mod 4) per row up
 #ifdef SWB_X_BTDEBUG
     long long dbg_walk = 0, dbg_total0 = clock64(); int dbg_bands = 0, dbg_miss = 0;
 #endif
@@ -1212,27 +1235,19 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
 #endif
             const int* band = bandbuf(cur);          // (not volatile: ptxas puts a YIELD into loops with volatile loads, ~150 clk per iteration)
             int* list = listbuf(cur);
-            long long r;
-            int sh = (int)(bt_row_start(bi, bc, pitch, kBtRows - 1, r) & 3);     // shift of the current row
-            int a = (kBtRows - 1) * kBtRS + sh + k0, cnt = 0;
+            int a = (kBtRows - 1) * kBtRS + k0, cnt = 0;
             int pv = band[a];
-            // step sizes in the staged band, packed by P code: DIAGONAL (:410) = one band row up,
-            // UP (:412) = one row up and one column right, LEFT (:414) = one column left; a row up
-            // also changes the shift from sh to (sh - nu) & 3
-            auto table = [&](int shift) {
-                const int d = ((shift - nu) & 3) - shift;
-                return (unsigned)((kBtRS - d) << 24 | 1 << 16 | (kBtRS - 1 - d) << 8);
-            };
-            unsigned tab = table(sh);
+            // step sizes in the staged band by P code (byte pv of the table): UP (:412) = one band row up and one
+            // column right, LEFT (:414) = one column left, DIAGONAL (:410) = one band row up (the band follows the
+            // diagonal); NONE, the marker and already negated cells select 0
+            constexpr unsigned kTab = (unsigned)(kBtRS - 1) << 8 | 1u << 16 | (unsigned)kBtRS << 24;
             while (true) {
                 // speculative: address and load of the successor are issued before pv is checked, so the
-                // branch resolves in the shadow of the load (for NONE / marker / negative values the step is 0)
-                const int a2 = a - (int)__byte_perm(tab, 0u, (unsigned)pv);
+                // branch resolves in the shadow of the load
+                const int a2 = a - (int)__byte_perm(kTab, 0u, (unsigned)pv);
                 const int pv2 = band[a2];
                 if ((unsigned)(pv - 1) >= 3u) break;
                 list[cnt++] = a;
-                sh = (pv & 1) ? ((sh - nu) & 3) : sh;                     // off the load chain
-                tab = table(sh);
                 a = a2; pv = pv2;
             }
             s_count[cur] = cnt;
@@ -1257,7 +1272,7 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
             const int rr = (a + kBtRS) / kBtRS - 1;               // -1 = the marker row above the band
             long long r;
             const long long s = bt_row_start(bi, bc, pitch, rr, r);
-            const long long g = s + (a - rr * kBtRS - (int)(s & 3));
+            const long long g = s + (a - rr * kBtRS);
             i = r; j = g - r * pitch;
         }
         if (s_done) break;                                        // (i, j) = the cell that ended the walk

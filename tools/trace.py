@@ -30,3 +30,12 @@ import numpy as np
 print("mean gate->gate lag between consecutive strips (us):", np.diff(t[:, 1]).mean())
 print("mean g4-gate (first 32 steps) us:", (t[:, 2] - t[:, 1]).mean(), " g8-g4 (next 32 steps):", (t[:, 3] - t[:, 2]).mean(),
       " end-g8 per step (ns):", ((t[:, 4] - t[:, 3]) * 1000 / ( (cols//4 + 32) - 64)).mean())
+g = t[:, 1]
+lag = np.diff(g)
+inner = lag[0::2]      # strip 2k -> 2k+1: same CTA (shared-memory ring)
+cross = lag[1::2]      # strip 2k+1 -> 2k+2: next band (global boundary row + loader)
+print("lag inside a CTA   : mean %.2f us  median %.2f  p90 %.2f  max %.2f" % (inner.mean(), np.median(inner), np.percentile(inner, 90), inner.max()))
+print("lag across bands   : mean %.2f us  median %.2f  p90 %.2f  max %.2f" % (cross.mean(), np.median(cross), np.percentile(cross, 90), cross.max()))
+for lo in range(0, strips - 1, max(1, strips // 8)):
+    hi = min(strips - 1, lo + max(1, strips // 8))
+    print("  strips %4d-%4d: mean lag %.2f us (inner %.2f, cross %.2f)" % (lo, hi, lag[lo:hi].mean(), lag[lo:hi][0::2].mean() if lo % 2 == 0 else lag[lo:hi][1::2].mean(), lag[lo:hi][1::2].mean() if lo % 2 == 0 else lag[lo:hi][0::2].mean()))
