@@ -92,6 +92,9 @@ constexpr int kBoundaryPad = 32;       // spare blocks in front of a band-bounda
 constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: compute warps on schedulers 0..wpc-1,
                                        // writers + loader on the others
 constexpr int kDrainRounds = 2;        // writer rounds after the last compute group
+#ifndef SWB_KMAX_IN_COMPUTE
+#define SWB_KMAX_IN_COMPUTE 1          // who keeps the strip maximum: the compute warp (1) or its writers (0)
+#endif
 // writer round r reads steps [8r-8, 8r+7]; compute group g overwrites the slots of group
 // g - KT/8, which rounds <= g - KT/8 + 1 read: g may start once that many rounds are done
 __host__ __device__ constexpr int stage_slack(int KT) { return KT / kGroup - 2; }
@@ -409,7 +412,7 @@ struct Strip {
             if (q == kR - 1) n3 = __shfl_up_sync(0xffffffffu, h3, 1);
 #endif
             hl[q] = h3;
-            if (STORE) {
+            if (STORE && SWB_KMAX_IN_COMPUTE) {
                 int e0 = k0, e1 = k1, e2 = k2, e3 = k3;
                 if (MODE & 1) e0 = (j == 0) ? 0 : k0;        // column 0 (blocks j < 0 hold NONE)
                 if (MODE & 2) {
@@ -420,6 +423,8 @@ struct Strip {
                     e3 = (c + 3 <= mcols) ? k3 : 0;
                 }
                 kmax = __vimax3_s32(__vimax3_s32(kmax, e0, e1), e2, e3);
+            }
+            if (STORE) {
                 // stage the packed block of this row for the writers
                 if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
                 if (q == 1) sts_int4<kRowInts * 4>(sa, k0, k1, k2, k3);
@@ -654,6 +659,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
     __syncwarp();
     const int* mystage = stage + (size_t)kWRows * sub * kRowInts;
 
+    int mx = 0;                                                   // largest key of my rows in columns 1..m
     const int rounds = p.ngroups + kDrainRounds;
     const int m = (int)p.m;
     const long long pdelta = (long long)(p.P - p.H);              // P[i] sits pdelta ints after H[i]
@@ -745,6 +751,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #ifndef SWB_X_NOSTG
                 SWB_ST(reinterpret_cast<int32_t*>(mad_wide(oo, one, hcol)), kk >> 4);
                 SWB_ST(reinterpret_cast<int32_t*>(mad_wide(oo, one, pcol)), kk & 3);
+                if (!SWB_KMAX_IN_COMPUTE) mx = max(mx, kk);
 #else
                 if (kk == 0x7ffffff1) __stcs(reinterpret_cast<int32_t*>(mad_wide(oo, one, hcol)), kk >> 4);
 #endif
@@ -759,6 +766,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                 const int k = mystage[l * kRowInts + ((v + tb.z) & (kRowInts - 1))];
                 __stcs(hp, k >> 4);
                 __stcs(hp + pdelta, k & 3);
+                if (!SWB_KMAX_IN_COMPUTE) mx = max(mx, k);
             }
         } else {
 #pragma unroll 2
@@ -773,6 +781,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                     // column-strip mode: local column 0 belongs to the GPU on the left; its P holds the
                     // hand-off marker that ends this GPU's part of the backtrack
                     __stcs(hp + pdelta, (c == 0 && p.left_in != nullptr) ? kHandOff : (k & 3));
+                    if (!SWB_KMAX_IN_COMPUTE && c > 0) mx = max(mx, k);
                     // ... and my last column is the boundary column of the GPU on the right (P2P store over NVLink)
                     if (c == m && p.right_out != nullptr)
                         asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.right_out + r0 + kWRows * sub + l), "r"(k >> 4) : "memory");
@@ -798,6 +807,11 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
         __syncwarp();
         if (lane == 0)
             asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p.right_flags + (r0 - 1) / kWRows + sub), "r"(p.epoch) : "memory");
+    }
+    if (!SWB_KMAX_IN_COMPUTE) {
+        // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel)
+        const int hm = __reduce_max_sync(0xffffffffu, mx) >> 4;
+        if (lane == 0 && hm > 0) { atomicMax(p.strip_max + strip, hm); atomicMax(p.gmax, hm); }
     }
 #if !defined(SWB_X_GROUPTRACE) && !defined(SWB_X_WRITERTRACE) && !defined(SWB_X_CLKTRACE)
     trace_stamp(p, strip, 5 + (sub & 1), lane);
@@ -969,7 +983,7 @@ fill_kernel(const FillParams p_in)
                       (unsigned)__cvta_generic_to_shared(s_drained + w * kWriters),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, strip + pair * p.nstrips);
-        if (STORE) {
+        if (STORE && SWB_KMAX_IN_COMPUTE) {
             // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel).  The rows past n of a
             // partial strip never match (inv), so their cells stay below the cells above them.
             const int mx = __reduce_max_sync(0xffffffffu, S.kmax) >> 4;
@@ -1241,6 +1255,9 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
             // column right, LEFT (:414) = one column left, DIAGONAL (:410) = one band row up (the band follows the
             // diagonal); NONE, the marker and already negated cells select 0
             constexpr unsigned kTab = (unsigned)(kBtRS - 1) << 8 | 1u << 16 | (unsigned)kBtRS << 24;
+            // (Tried: loading the eight cells reachable within two moves at once and resolving both moves with
+            // selects -- 90 clk per cell instead of 68: a single thread pays several cycles per instruction, so the
+            // walk is bound by its instruction count, not by the load.)
             while (true) {
                 // speculative: address and load of the successor are issued before pv is checked, so the
                 // branch resolves in the shadow of the load
