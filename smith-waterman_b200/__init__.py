@@ -167,10 +167,11 @@ def fill_batch_async(a, m: int, b, n: int, npairs: int, dH, dP, pitch: int | Non
 
 
 def score_only_async(a, m: int, b, n: int, npairs: int = 1, d_maxPos=None, d_maxScore=None, scoring=None,
-                     device: int = 0, stream=None, warps_per_band: int = 0, timer=None) -> None:
+                     device: int = 0, stream=None, warps_per_band: int = 0, timer=None, trace=None) -> None:
     """Enqueue the score-only kernel (no H/P stores) for npairs equally shaped pairs."""
     sc = _scoring(scoring)
-    tun = Tuning(warps_per_band=warps_per_band, timer=timer._h if timer is not None else None)
+    tun = Tuning(warps_per_band=warps_per_band, timer=timer._h if timer is not None else None,
+                 trace=_ptr(trace) if trace is not None else None)
     _check(lib.swb_score_only_async(_ptr(a), m, _ptr(b), n, npairs, C.byref(sc), _ptr(d_maxPos), _ptr(d_maxScore), device,
                                     _stream_ptr(stream), C.byref(tun)))
 

@@ -50,9 +50,10 @@ int check_scoring(const swb_scoring& sc, int64_t m, int64_t n)
     if (std::llabs((long long)sc.match) > lim || std::llabs((long long)sc.mismatch) > lim ||
         std::llabs((long long)sc.gap) > lim)
         return SWB_ERR_RANGE;
-    // a gap must cost something: the fill relies on H = 0 / NONE being what a cell with all-zero neighbours evaluates to
-    // (with gap >= 0 the scores are not bounded by match * min(m,n) either)
-    if (sc.gap >= 0) return SWB_ERR_RANGE;
+    // a gap must cost something and a mismatch must not pay: the fill relies on H = 0 / NONE being what a cell with
+    // all-zero neighbours and a non-matching character evaluates to (with gap >= 0 the scores are not bounded by
+    // match * min(m,n) either)
+    if (sc.gap >= 0 || sc.mismatch > 0) return SWB_ERR_RANGE;
     // packed keys are 16*H + tie in int32; H <= match * min(m,n)
     const int64_t hmax = (int64_t)std::max(sc.match, 0) * std::min(m, n);
     if (hmax >= (1LL << 26)) return SWB_ERR_RANGE;

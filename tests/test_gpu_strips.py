@@ -46,7 +46,7 @@ def check_against_oracle(sset, oracle, a, b):
     return starts
 
 
-@pytest.mark.parametrize("m,n,nstrips", [(300, 200, 2), (1027, 700, 3), (2000, 3000, 4), (130, 1500, 2), (4100, 260, 8)])
+@pytest.mark.parametrize("m,n,nstrips", [(300, 200, 2), (1027, 700, 3), (2000, 3000, 4), (130, 1500, 2), (4100, 260, 8), (40, 300, 8), (9, 70, 3)])
 def test_strips_on_one_device(swb, strips, oracle, m, n, nstrips):
     a, b = make_pair(m + n, m, n)
     sset = strips.StripSet(a, b, nstrips)

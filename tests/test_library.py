@@ -79,3 +79,29 @@ def test_schedule_model_reproduces_oracle(oracle, m, n, wpc, pitch, policy):
     from schedule_model import STRIP_ROWS
     want = [H[1 + STRIP_ROWS * s: 1 + STRIP_ROWS * (s + 1)].max() for s in range((n + STRIP_ROWS - 1) // STRIP_ROWS)]
     assert list(smax) == want
+
+
+def test_argument_checks_come_before_any_cuda_call(swb):
+    """Bad arguments are rejected with a status code, never a crash or an exit ('all return int'); these
+    checks run before the first CUDA call, so they work without a device."""
+    import ctypes as C
+    buf = (C.c_char * 64)()
+    out = (C.c_int32 * 64)()          # stands in for device pointers: never dereferenced on these paths
+    a = b = C.addressof(buf)
+    H = P = (C.addressof(out) + 15) // 16 * 16
+
+    def fill(m, n, scoring, dH=H, dP=P, pitch=None):
+        sc = swb.Scoring(*scoring)
+        return swb.lib.swb_fill_async(a, m, b, n, C.byref(sc), dH, dP, pitch or m + 1, None, None, 0, None, None)
+
+    ARG, RANGE, ALIGN = -1, swb.lib.swb_fill_async(a, 1 << 30, b, 8, None, H, P, (1 << 30) + 1, None, None, 0, None, None), None
+    assert fill(0, 8, (3, -3, -2)) == ARG and fill(8, -1, (3, -3, -2)) == ARG
+    assert fill(8, 8, (3, -3, -2), dH=None) == ARG and fill(8, 8, (3, -3, -2), pitch=8) == ARG
+    assert RANGE not in (0, ARG)
+    assert fill(8, 8, (3, -3, 0)) == RANGE            # a gap must cost something
+    assert fill(8, 8, (3, 1, -2)) == RANGE            # mismatch <= 0
+    assert fill(8, 8, (1 << 21, -3, -2)) == RANGE
+    assert fill(8, 8, (3, -3, -2), dH=H + 4) not in (0, ARG, RANGE)      # 16-byte alignment of H / P
+    assert swb.lib.swb_strip_flag_count(0) == 0 and swb.lib.swb_strip_flag_count(33) == 2 and swb.lib.swb_strip_flag_count(64) == 2
+    for code in (0, ARG, RANGE):
+        assert len(swb.lib.swb_strerror(code)) > 0
