@@ -41,7 +41,10 @@
 #include <stdio.h>
 
 #ifndef SWB_X_GATESLEEP
-#define SWB_X_GATESLEEP 100
+#define SWB_X_GATESLEEP 0              // (no sleep at the gate either: see wait_block)
+#endif
+#ifndef SWB_X_LOADERSPINS
+#define SWB_X_LOADERSPINS 512
 #endif
 #ifndef SWB_X_WRITERSLEEP
 #define SWB_X_WRITERSLEEP 64
@@ -227,12 +230,12 @@ __device__ __forceinline__ void wait_block(unsigned ring_in, int x)
 {
     const unsigned a = ring_in + 16u * (unsigned)((x + 32) & (kRing - 1));
     const int want = 1 + (((x + 32) >> 6) & 1);
+    // Pure spin: __nanosleep oversleeps by microseconds on this hardware whatever its argument.  With a
+    // `nanosleep(20)` after 64 polls here a strip that followed its producer closely fell into a mode of one sleep
+    // per run of steps (1400 clk per step instead of 250) and dragged every later strip with it: score-only launches
+    // took 12 or 18 ms instead of 5.8, at random.
     int v = lds_volatile_int(a);
-    int spins = 0;
-    while ((v & 3) != want) {
-        if (++spins > 64) __nanosleep(20);
-        v = lds_volatile_int(a);
-    }
+    while ((v & 3) != want) v = lds_volatile_int(a);
 }
 __device__ __forceinline__ unsigned long long mad_wide(unsigned a, unsigned b, unsigned long long c)
 {
@@ -496,7 +499,7 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
     // first input block (block 0 -> ring index 32, epoch 0 -> tag 1); all lanes poll
     if (S.has_in) {
         int4 v = lds_volatile_int4<16 * 32>(S.ring_in);
-        while ((v.x & 3) != 1) { __nanosleep(SWB_X_GATESLEEP); v = lds_volatile_int4<16 * 32>(S.ring_in); }
+        while ((v.x & 3) != 1) { if (SWB_X_GATESLEEP > 0) __nanosleep(SWB_X_GATESLEEP); v = lds_volatile_int4<16 * 32>(S.ring_in); }
         if (lane == 0) { S.A0 = v.x & ~15; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w; }
     }
     trace_stamp(p, strip, 1, lane);
@@ -841,7 +844,9 @@ __device__ __forceinline__ void loader_band(const int4* src, const int nblocks, 
         // blocks enter the ring in order (the consumer polls only the last block of a run of steps)
         if (lane < lead) sts_volatile_int4(ring + ((j + 32) & (kRing - 1)), v);
         base += lead;
-        if (lead == 0) { if (++idle > 2) __nanosleep(idle > 64 ? 400 : 60); } else idle = 0;
+        // (polls without sleeping while the band above is producing: a sleep here is microseconds of lag on the fill's
+        // critical chain; after a long silence the band above has not started yet and the loader backs off)
+        if (lead == 0) { if (++idle > SWB_X_LOADERSPINS) __nanosleep(100); } else idle = 0;
     }
 }
 
