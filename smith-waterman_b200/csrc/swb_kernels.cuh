@@ -46,6 +46,10 @@
 #ifndef SWB_X_LOADERSPINS
 #define SWB_X_LOADERSPINS 512
 #endif
+#ifndef SWB_X_GT_LO
+#define SWB_X_GT_LO 8                   // SWB_X_GROUPTRACE: groups [LO, HI) are accumulated as "steady"
+#define SWB_X_GT_HI 0x7fffffff
+#endif
 #ifndef SWB_X_WRITERSLEEP
 #define SWB_X_WRITERSLEEP 64
 #endif
@@ -549,7 +553,7 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
             known_consumed = c;
         }
 #ifdef SWB_X_GROUPTRACE
-        if (g >= 8) { const long long gd2 = clock64(); dbg_drain += gd1 - gd0; dbg_cons += gd2 - gd1; }
+        if (g >= SWB_X_GT_LO && g < SWB_X_GT_HI) { const long long gd2 = clock64(); dbg_drain += gd1 - gd0; dbg_cons += gd2 - gd1; }
 #endif
         sts_volatile_int_if(consumed_in, t0, S.has_in & (lane == 0 ? 1 : 0));
         // ---- sequence words of the next group
@@ -604,7 +608,7 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         if (STORE) sts_volatile_int_if(staged, g + 1, lane == 0 ? 1 : 0);
 #ifdef SWB_X_GROUPTRACE
         { const long long gc3 = clock64();
-          if (g >= 8) { dbg_pre += gc1 - gc0; dbg_steps += gc2 - gc1; dbg_post += gc3 - gc2; ++dbg_n; }
+          if (g >= SWB_X_GT_LO && g < SWB_X_GT_HI) { dbg_pre += gc1 - gc0; dbg_steps += gc2 - gc1; dbg_post += gc3 - gc2; ++dbg_n; }
           else if (g < 4) { dbg_e_steps += gc2 - gc1; dbg_e_other += (gc1 - gc0) + (gc3 - gc2); } }
 #endif
     }
