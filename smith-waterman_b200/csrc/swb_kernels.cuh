@@ -1162,25 +1162,39 @@ __device__ __forceinline__ long long bt_row_start(long long i0, long long c0, lo
 
 // prefetch warps only.  limit = number of valid ints of P the kernel may read.
 __device__ __forceinline__ void bt_fetch_band(int* buf, const int32_t* P, long long pitch, long long limit,
-                                              long long i0, long long c0)
+                                              long long i0, long long c0, unsigned long long* mbar, unsigned& phase)
 {
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
+    // One TMA bulk copy per band row (528 bytes from the 16-byte aligned global element at or before the row's first
+    // column), issued by the first kBtRows fetcher threads and counted by an mbarrier.  The earlier version -- 33
+    // cp.async of 16 bytes per row -- kept the SM's load/store pipeline so busy that every load of the walker took
+    // about twice the shared-memory latency.
     const int tid = threadIdx.x - 32;
-    for (int e = tid; e < kBtRows * (kBtRS / 4); e += kBtFetchers) {
-        const int rr = e / (kBtRS / 4), ch = e % (kBtRS / 4);
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+    if (tid < kBtRows) {
+        const int rr = tid;
         long long r;
         const long long s = bt_row_start(i0, c0, pitch, rr, r);
-        const long long g0 = (s & ~3LL) + 4 * ch;                 // aligned global index of this chunk
-        int* dst = buf + rr * kBtRS + 4 * ch;
-        if (r >= 0 && g0 >= 0 && g0 + 4 <= limit) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 4u * (unsigned)(rr * kBtRS + 4 * ch)), "l"(P + g0) : "memory");
+        const long long g0 = s & ~3LL;                             // aligned global index of the row's first chunk
+        int* dst = buf + rr * kBtRS;
+        if (r >= 0 && g0 >= 0 && g0 + kBtRS <= limit) {
+            const unsigned sd = (unsigned)__cvta_generic_to_shared(dst);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the buffer was last touched through the generic proxy
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(kBtRS * 4) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sd), "l"(P + g0), "r"(kBtRS * 4), "r"(mb) : "memory");
         } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = (r >= 0 && g0 + k >= 0 && g0 + k < limit) ? P[g0 + k] : 0;
+            for (int k = 0; k < kBtRS; ++k) dst[k] = (r >= 0 && g0 + k >= 0 && g0 + k < limit) ? P[g0 + k] : 0;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
         }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                         : "=r"(done) : "r"(mb), "r"(phase) : "memory");
+        }
+        phase ^= 1u;
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(kBtFetchers) : "memory");
     // A row landed with its first band column at offset (row start & 3): shift every row into place (one warp per
     // row, in place: all loads of the row precede its stores), so that band column k of band row rr is
@@ -1221,6 +1235,14 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
     extern __shared__ __align__(16) int bt_smem[];      // 2 x (pad + 128x132 ints), then 2 lists
     __shared__ long long s_len;
     __shared__ int s_done, s_a, s_count[2];
+    __shared__ __align__(8) unsigned long long s_mbar[2];     // one per band buffer: counts the rows of a fetch
+    unsigned mphase[2] = {0u, 0u};
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 2; ++k)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[k])), "r"(kBtRows) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const long long pos = d_maxPos ? *d_maxPos : maxPos_arg;
     if (pos <= 0) { if (threadIdx.x == 0) { if (d_pathLen) *d_pathLen = 0; if (d_endPos) *d_endPos = 0; } return; }
     long long i = pos / pitch, j = pos % pitch;         // current cell
@@ -1239,7 +1261,7 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
 #ifdef SWB_X_BTDEBUG
     long long dbg_walk = 0, dbg_total0 = clock64(); int dbg_bands = 0, dbg_miss = 0;
 #endif
-    if (fetcher) bt_fetch_band(bandbuf(cur), P, pitch, limit, bi, bc);
+    if (fetcher) bt_fetch_band(bandbuf(cur), P, pitch, limit, bi, bc, &s_mbar[cur], mphase[cur]);
     __syncthreads();
     int k0 = kBtCols / 2;                               // band column of the current cell (bottom row)
     while (true) {
@@ -1250,7 +1272,7 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
 #else
         if (fetcher) {
             if (have_prev) bt_writeback(bandbuf(cur ^ 1), listbuf(cur ^ 1), s_count[cur ^ 1], P, pitch, pbi, pbc);
-            bt_fetch_band(bandbuf(cur ^ 1), P, pitch, limit, ni, nc);
+            bt_fetch_band(bandbuf(cur ^ 1), P, pitch, limit, ni, nc, &s_mbar[cur ^ 1], mphase[cur ^ 1]);
         } else if (walker) {
 #endif
 #ifdef SWB_X_BTDEBUG
@@ -1288,7 +1310,7 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
 #ifdef SWB_X_BTSERIAL
         if (fetcher) {
             if (have_prev) bt_writeback(bandbuf(cur ^ 1), listbuf(cur ^ 1), s_count[cur ^ 1], P, pitch, pbi, pbc);
-            bt_fetch_band(bandbuf(cur ^ 1), P, pitch, limit, ni, nc);
+            bt_fetch_band(bandbuf(cur ^ 1), P, pitch, limit, ni, nc, &s_mbar[cur ^ 1], mphase[cur ^ 1]);
         }
         __syncthreads();
 #endif
@@ -1317,7 +1339,7 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
             if (fetcher) {
                 bt_writeback(bandbuf(cur), listbuf(cur), s_count[cur], P, pitch, pbi, pbc);
                 bi = i; bc = j;
-                bt_fetch_band(bandbuf(cur), P, pitch, limit, bi, bc);
+                bt_fetch_band(bandbuf(cur), P, pitch, limit, bi, bc, &s_mbar[cur], mphase[cur]);
             }
             have_prev = false;
             bi = i; bc = j;
