@@ -147,9 +147,19 @@ struct FillParams {
     int             epoch;
 };
 
+// Developer builds only (-DSWB_TRACE, `make trace` -> build/libswb200_trace.so, used by tools/trace.py and friends):
+// the product library ignores swb_tuning.trace -- the checks alone were ~20 instructions per group of 8 steps on the
+// compute warps.
+#ifndef SWB_TRACE
+#if defined(SWB_X_GROUPTRACE) || defined(SWB_X_WRITERTRACE) || defined(SWB_X_CLKTRACE)
+#define SWB_TRACE 1
+#else
+#define SWB_TRACE 0
+#endif
+#endif
 __device__ __forceinline__ void trace_stamp(const FillParams& p, long long strip, int slot, int lane)
 {
-    if (p.trace && lane == 0) {
+    if (SWB_TRACE && p.trace && lane == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[strip * 8 + slot] = t;
@@ -521,8 +531,7 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 #endif
     for (int g = 0; g < p.ngroups; ++g) {
 #ifndef SWB_X_GROUPTRACE
-        if (g == 4) trace_stamp(p, strip, 2, lane);
-        if (g == 8) trace_stamp(p, strip, 3, lane);
+        if (SWB_TRACE && p.trace != nullptr && (g == 4 || g == 8)) trace_stamp(p, strip, g == 4 ? 2 : 3, lane);
 #endif
         const int t0 = g * kGroup;
 #ifdef SWB_X_GROUPTRACE
@@ -583,20 +592,33 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
             const int xb = min(t0 + kWaitSteps * ((H) + 1), p.jmax);                                      \
             if (xb > t0 + kWaitSteps * (H)) wait_block(S.ring_in, xb);                                    \
         }
+        // the same for a group that ends before jmax: block t0+4 sits four entries after block t0 (no wrap: t0 is a
+        // multiple of 8) in the same epoch, block t0+8 is the entry the last step polls anyway
+#define SWB_WAITF(H)                                                                                      \
+        if (S.has_in) {                                                                                   \
+            if (kWaitSteps == 4 && (H) == 0) { while ((lds_volatile_int(in_g + 64u) & 3) != want) { } }  \
+            else                             { while ((lds_volatile_int(in_w) & 3) != want_w) { } }       \
+        }
 #define SWB_STEP(E, I) S.template step<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w)
         // forced = b holds a NUL byte, or column-strip mode (boundary injection): head and tail steps differ.
         // Otherwise a full fill runs the interior step everywhere; score only still masks the columns past m.
-#define SWB_GROUP(M) { SWB_WAIT(0) SWB_STEP(M, 0); SWB_STEP(M, 1); SWB_STEP(M, 2); SWB_STEP(M, 3);  \
-                       if (kWaitSteps == 4) { SWB_WAIT(1) }                                          \
-                       SWB_STEP(M, 4); SWB_STEP(M, 5); SWB_STEP(M, 6); SWB_STEP(M, 7); }
-        const bool head = forced && g < 4, tail = (forced || !STORE) && g > gtail;
-        if (!head && !tail) SWB_GROUP(0)
-        else if (head && !tail) SWB_GROUP(1)
-        else if (tail && !head) SWB_GROUP(2)
-        else SWB_GROUP(3)
+#define SWB_GROUP(M, W) { W(0) SWB_STEP(M, 0); SWB_STEP(M, 1); SWB_STEP(M, 2); SWB_STEP(M, 3);       \
+                          if (kWaitSteps == 4) { W(1) }                                               \
+                          SWB_STEP(M, 4); SWB_STEP(M, 5); SWB_STEP(M, 6); SWB_STEP(M, 7); }
+        // (only in the single-pair full-fill instantiation: the others are compiled for two CTAs per SM and have no
+        // registers to spare for a fifth copy of the group)
+        if ((KT == 64 && STORE) && g <= gtail && !(forced && g < 4)) SWB_GROUP(0, SWB_WAITF)
+        else {
+            const bool head = forced && g < 4, tail = (forced || !STORE) && g > gtail;
+            if (!head && !tail) SWB_GROUP(0, SWB_WAIT)
+            else if (head && !tail) SWB_GROUP(1, SWB_WAIT)
+            else if (tail && !head) SWB_GROUP(2, SWB_WAIT)
+            else SWB_GROUP(3, SWB_WAIT)
+        }
 #undef SWB_GROUP
 #undef SWB_STEP
 #undef SWB_WAIT
+#undef SWB_WAITF
 #ifdef SWB_X_GROUPTRACE
         const long long gc2 = clock64();
 #endif

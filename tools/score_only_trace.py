@@ -1,5 +1,6 @@
 """Developer tool: strip timeline of the score-only kernel for a few launches (fast and slow ones)."""
-import importlib, sys, torch, numpy as np
+import importlib, os, sys, torch, numpy as np
+os.environ.setdefault("SWB_LIB", "build/libswb200_trace.so")   # make -C smith-waterman_b200 trace
 sys.path.insert(0, '.')
 swb = importlib.import_module("smith-waterman_b200")
 dev = torch.device("cuda:0")

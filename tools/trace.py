@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Developer tool: per-strip globaltimer stamps of the fill kernel (swb_tuning.trace).
   python tools/trace.py --shape 8192x8192 --wpc 2"""
-import argparse, importlib, sys
+import argparse, importlib, os, sys
+os.environ.setdefault("SWB_LIB", "build/libswb200_trace.so")   # make -C smith-waterman_b200 trace
 from pathlib import Path
 import torch
 ROOT = Path(__file__).resolve().parents[1]
