@@ -377,11 +377,17 @@ struct Strip {
     {
         constexpr bool LAST = (I == kGroup - 1);
         const int j = t - lane;
-        const bool poll = has_in && (!(MODE & 2) || t + 1 <= jmax);
-        // block t+1 of the strip above (the row above lane 0's first row in the next step):
-        // first try early, it is needed only after the shuffles
-        int4 v = make_int4(0, 0, 0, 0);
-        if (poll) v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
+        // block t+1 of the strip above (the row above lane 0's first row in the next step): loaded early, it is needed
+        // only after the shuffles.  Unconditional outside the tail: the first strip of a pair reads its zero-filled
+        // ring (a predicated load cost eight extra moves per step), and past the end of the row above the ring holds
+        // stale blocks that only reach columns > m.
+        int4 v;
+        if (MODE & 2) {
+            v = make_int4(0, 0, 0, 0);
+            if (has_in && t + 1 <= jmax) v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
+        } else {
+            v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
+        }
 
         // K = max(left+gap|LEFT, up+gap|UP, diag+s|DIAG, 0|NONE)     (omp_smithW.c:339-381)
         int u0 = A0, u1 = A1, u2 = A2, u3 = A3, dg = dgp;
