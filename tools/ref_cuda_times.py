@@ -41,3 +41,22 @@ for n in (int(x) for x in args.sizes.split(",")):
         except subprocess.TimeoutExpired:
             ref[name] = f">{args.timeout:.0f} s"
     print(f"{n:>7} | {min(ks):15.3f} ms | {e2e:19.1f} ms | {ref['simple_cuda_ref']:>17} | {ref['rotated_cuda_ref']:>17}", flush=True)
+
+# the configuration the authors published (omp_smithW-v1-refinedOrig.cpp -DSKIP_BACKTRACK=1: no maxPos, no critical
+# section) on all host cores, and the plain reference with 1 thread (its per-cell `omp critical` makes threads a loss)
+import os
+print(f"\nCPU comparators on this host ({os.cpu_count()} cpus): seconds of 'Elapsed time for scoring matrix computation'")
+for n in (2048, 8192):
+    row = [f"{n:>7}"]
+    for name, env in (("v1_skipbt_ref", {}), ("omp_smithW_ref", {"OMP_NUM_THREADS": "1"})):
+        exe = ROOT / "oracle" / "_ref" / name
+        if not exe.exists():
+            row.append(f"{name}: not built"); continue
+        try:
+            out = subprocess.run([str(exe), str(n), str(n)], capture_output=True, text=True, timeout=args.timeout, env={**os.environ, **env})
+            mm = re.search(r"scoring matrix computation:\s*([0-9.]+)", out.stdout)
+            sec = float(mm.group(1)) if mm else float("nan")
+            row.append(f"{name}{' (1 thread)' if env else ' (all cores)'}: {sec:.3f} s = {n * n / sec / 1e9:.3f} GCUPS")
+        except subprocess.TimeoutExpired:
+            row.append(f"{name}: >{args.timeout:.0f} s")
+    print(" | ".join(row), flush=True)
