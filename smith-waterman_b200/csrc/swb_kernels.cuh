@@ -792,8 +792,33 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #endif
             }
 #endif
+        } else if (KT == 32 && p.left_in == nullptr && p.right_out == nullptr) {
+            // Edge rounds (for some rows part of the round lies left of column 0 or right of column m) and the partial
+            // last strip of a pair: batches of 8 rows with predicated stores.  For small matrices most rounds are edge
+            // rounds (9 of 12 at 256 columns: the 65536 x 256x256 batch went from 302 to 355 GCUPS with this path).
+            // Batch instantiation only: in the single-pair kernel the same path made the 45000x45000 fill 8 % SLOWER
+            // (5.0 -> 5.4 ms; the row-by-row loop below spreads the first rounds' stores of a strip thinner).
+#pragma unroll 1
+            for (int l0 = 0; l0 < kWRows; l0 += 8) {
+                int k[8]; int32_t* hp[8]; bool ok[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int4 tb = rowtab[l0 + i];                                    // (pointer, F, E)
+                    hp[i] = reinterpret_cast<int32_t*>(((unsigned long long)(unsigned)tb.y << 32) | (unsigned)tb.x) + v;
+                    ok[i] = ((rowmask >> (l0 + i)) & 1u) && (unsigned)(v - tb.w) <= (unsigned)m;
+                    k[i] = mystage[(l0 + i) * kRowInts + ((v + tb.z) & (kRowInts - 1))];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (ok[i]) {
+                        SWB_ST(hp[i], k[i] >> 4);
+                        SWB_ST(hp[i] + pdelta, k[i] & 3);
+                        if (!SWB_KMAX_IN_COMPUTE) mx = max(mx, k[i]);          // (column 0 holds NONE = 8 >> 4 = 0)
+                    }
+                }
+            }
         } else if (interior) {
-            // partial strip (the last one of a pair): same, row by row
+            // column-strip mode, partial strip (the last one of a pair): row by row
 #pragma unroll 2
             for (int l = 0; l < nvalid; ++l) {
                 const int4 tb = rowtab[l];
