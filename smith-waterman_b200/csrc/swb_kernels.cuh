@@ -760,10 +760,50 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
             // batches of 8 rows: all table and data loads first, then the 16 stores.  Per row the ALU pipe
             // sees the ring index (2 ops) and the unpacking (2 ops); the two addresses are one IMAD.WIDE each
             // (row offset in bytes * 1 + the 64-bit address of this lane's column in the strip's first row)
-            const unsigned long long hcol = hbase + 4ull * (unsigned)v, pcol = hcol + 4ull * (unsigned long long)pdelta;
 #ifndef SWB_WRITER_DEPTH
 #define SWB_WRITER_DEPTH 4
 #endif
+#ifndef SWB_WRITER_PAIRS
+#define SWB_WRITER_PAIRS 1
+#endif
+#if SWB_WRITER_PAIRS
+            // Two rows per store instruction: a half-warp covers the 32 columns of one row with 8-byte stores (every
+            // row's window starts on a 128-byte line, so two adjacent columns are 8-byte aligned), lanes 0-15 row 2i,
+            // lanes 16-31 row 2i+1.  Same bytes, same shared-memory loads, half the STG instructions in the SM's
+            // load/store pipeline (which the compute warps' shuffles share).
+            const int half = lane >> 4;
+            const int vv = 32 * r + 2 * (lane & 15);                  // my two columns of the window: vv, vv + 1
+            const unsigned long long hcol = hbase + 4ull * (unsigned)vv, pcol = hcol + 4ull * (unsigned long long)pdelta;
+            constexpr int D = SWB_WRITER_DEPTH;
+            int ka[D], kb[D]; unsigned off[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const int row = 2 * i + half;
+                const int2 tb = rowoff[row];
+                off[i] = (unsigned)tb.x;
+                ka[i] = mystage[row * kRowInts + ((vv + tb.y) & (kRowInts - 1))];
+                kb[i] = mystage[row * kRowInts + ((vv + 1 + tb.y) & (kRowInts - 1))];
+            }
+#pragma unroll
+            for (int i = 0; i < kWRows / 2; ++i) {
+                const int xa = ka[i % D], xb = kb[i % D]; const unsigned oo = off[i % D];
+                if (i + D < kWRows / 2) {
+                    const int row = 2 * (i + D) + half;
+                    const int2 tb = rowoff[row];
+                    off[i % D] = (unsigned)tb.x;
+                    ka[i % D] = mystage[row * kRowInts + ((vv + tb.y) & (kRowInts - 1))];
+                    kb[i % D] = mystage[row * kRowInts + ((vv + 1 + tb.y) & (kRowInts - 1))];
+                }
+#ifndef SWB_X_NOSTG
+                __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, hcol)), make_int2(xa >> 4, xb >> 4));
+                __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, pcol)), make_int2(xa & 3, xb & 3));
+                if (!SWB_KMAX_IN_COMPUTE) mx = max(mx, max(xa, xb));
+#else
+                if (xa == 0x7ffffff1) __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, hcol)), make_int2(xa >> 4, xb >> 4));
+#endif
+            }
+#else
+            const unsigned long long hcol = hbase + 4ull * (unsigned)v, pcol = hcol + 4ull * (unsigned long long)pdelta;
             // rolling pipeline over the rows: the loads of row i+D are issued before the two stores of row i, so the
             // stores leave the SM as a steady trickle.  (Batches of 8 rows = bursts of 16 STGs: the shuffles and
             // shared-memory accesses on the compute warps' chain queue behind them in the SM's load/store pipeline.)
@@ -791,6 +831,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                 if (kk == 0x7ffffff1) __stcs(reinterpret_cast<int32_t*>(mad_wide(oo, one, hcol)), kk >> 4);
 #endif
             }
+#endif
 #endif
         } else if (KT == 32 && p.left_in == nullptr && p.right_out == nullptr) {
             // Edge rounds (for some rows part of the round lies left of column 0 or right of column m) and the partial
