@@ -93,7 +93,10 @@ constexpr int kGroup    = 8;           // steps per synchronisation group
 #ifndef SWB_WAIT_STEPS
 #define SWB_WAIT_STEPS 4
 #endif
-constexpr int kWaitSteps = SWB_WAIT_STEPS;   // steps per poll of the strip above (4 or 8)
+constexpr int kWaitSteps = SWB_WAIT_STEPS;   // steps per poll of the strip above (4 or 8); the single-pair full fill uses 8
+#ifndef SWB_WAIT_STEPS_SINGLE
+#define SWB_WAIT_STEPS_SINGLE 8        // measured: 45000x45000 4.99 -> 4.89 ms, 100000x100000 18.7 -> 18.5 ms; the batch and
+#endif                                 // score-only instantiations are 2 % faster with 4
 constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
 constexpr int kBoundaryPad = 32;       // spare blocks in front of a band-boundary row (blocks -31..-1 of a strip's first steps)
 constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: compute warps on schedulers 0..wpc-1,
@@ -590,26 +593,27 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 #ifdef SWB_X_GROUPTRACE
         const long long gc1 = clock64();
 #endif
-        // The strip above is polled once per run of kWaitSteps steps, for the LAST block the run needs (the
-        // producer publishes its blocks in order); inside a run there is no branch.  This costs kWaitSteps
+        constexpr int kW = (KT == 64 && STORE) ? SWB_WAIT_STEPS_SINGLE : kWaitSteps;
+        // The strip above is polled once per run of kW steps, for the LAST block the run needs (the
+        // producer publishes its blocks in order); inside a run there is no branch.  This costs kW
         // steps of extra lag behind the producer and saves a third of every step.
 #define SWB_WAIT(H)                                                                                       \
         if (S.has_in) {                                                                                   \
-            const int xb = min(t0 + kWaitSteps * ((H) + 1), p.jmax);                                      \
-            if (xb > t0 + kWaitSteps * (H)) wait_block(S.ring_in, xb);                                    \
+            const int xb = min(t0 + kW * ((H) + 1), p.jmax);                                      \
+            if (xb > t0 + kW * (H)) wait_block(S.ring_in, xb);                                    \
         }
         // the same for a group that ends before jmax: block t0+4 sits four entries after block t0 (no wrap: t0 is a
         // multiple of 8) in the same epoch, block t0+8 is the entry the last step polls anyway
 #define SWB_WAITF(H)                                                                                      \
         if (S.has_in) {                                                                                   \
-            if (kWaitSteps == 4 && (H) == 0) { while ((lds_volatile_int(in_g + 64u) & 3) != want) { } }  \
+            if (kW == 4 && (H) == 0) { while ((lds_volatile_int(in_g + 64u) & 3) != want) { } }  \
             else                             { while ((lds_volatile_int(in_w) & 3) != want_w) { } }       \
         }
 #define SWB_STEP(E, I) S.template step<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w)
         // forced = b holds a NUL byte, or column-strip mode (boundary injection): head and tail steps differ.
         // Otherwise a full fill runs the interior step everywhere; score only still masks the columns past m.
 #define SWB_GROUP(M, W) { W(0) SWB_STEP(M, 0); SWB_STEP(M, 1); SWB_STEP(M, 2); SWB_STEP(M, 3);       \
-                          if (kWaitSteps == 4) { W(1) }                                               \
+                          if (kW == 4) { W(1) }                                               \
                           SWB_STEP(M, 4); SWB_STEP(M, 5); SWB_STEP(M, 6); SWB_STEP(M, 7); }
         // (only in the single-pair full-fill instantiation: the others are compiled for two CTAs per SM and have no
         // registers to spare for a fifth copy of the group)
