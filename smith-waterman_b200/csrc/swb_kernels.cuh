@@ -103,8 +103,11 @@ constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: com
                                        // writers + loader on the others
 constexpr int kDrainRounds = 2;        // writer rounds after the last compute group
 #ifndef SWB_KMAX_IN_COMPUTE
-#define SWB_KMAX_IN_COMPUTE 1          // who keeps the strip maximum: the compute warp (1) or its writers (0)
+#define SWB_KMAX_IN_COMPUTE 1          // who keeps the strip maximum: the compute warp (1) or its writers (0); the single-pair
+                                       // full fill (KT == 64) always leaves it to the writers: 1 % faster there, while the
+                                       // batch instantiation spills registers with it (SWB_KMAXC below)
 #endif
+#define SWB_KMAXC (SWB_KMAX_IN_COMPUTE && KT != 64)
 // writer round r reads steps [8r-8, 8r+7]; compute group g overwrites the slots of group
 // g - KT/8, which rounds <= g - KT/8 + 1 read: g may start once that many rounds are done
 __host__ __device__ constexpr int stage_slack(int KT) { return KT / kGroup - 2; }
@@ -438,7 +441,7 @@ struct Strip {
             if (q == kR - 1) n3 = __shfl_up_sync(0xffffffffu, h3, 1);
 #endif
             hl[q] = h3;
-            if (STORE && SWB_KMAX_IN_COMPUTE) {
+            if (STORE && SWB_KMAXC) {
                 int e0 = k0, e1 = k1, e2 = k2, e3 = k3;
                 if (MODE & 1) e0 = (j == 0) ? 0 : k0;        // column 0 (blocks j < 0 hold NONE)
                 if (MODE & 2) {
@@ -801,7 +804,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #ifndef SWB_X_NOSTG
                 __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, hcol)), make_int2(xa >> 4, xb >> 4));
                 __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, pcol)), make_int2(xa & 3, xb & 3));
-                if (!SWB_KMAX_IN_COMPUTE) mx = max(mx, max(xa, xb));
+                if (!SWB_KMAXC) mx = max(mx, max(xa, xb));
 #else
                 if (xa == 0x7ffffff1) __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, hcol)), make_int2(xa >> 4, xb >> 4));
 #endif
@@ -830,7 +833,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #ifndef SWB_X_NOSTG
                 SWB_ST(reinterpret_cast<int32_t*>(mad_wide(oo, one, hcol)), kk >> 4);
                 SWB_ST(reinterpret_cast<int32_t*>(mad_wide(oo, one, pcol)), kk & 3);
-                if (!SWB_KMAX_IN_COMPUTE) mx = max(mx, kk);
+                if (!SWB_KMAXC) mx = max(mx, kk);
 #else
                 if (kk == 0x7ffffff1) __stcs(reinterpret_cast<int32_t*>(mad_wide(oo, one, hcol)), kk >> 4);
 #endif
@@ -858,7 +861,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                     if (ok[i]) {
                         SWB_ST(hp[i], k[i] >> 4);
                         SWB_ST(hp[i] + pdelta, k[i] & 3);
-                        if (!SWB_KMAX_IN_COMPUTE) mx = max(mx, k[i]);          // (column 0 holds NONE = 8 >> 4 = 0)
+                        if (!SWB_KMAXC) mx = max(mx, k[i]);          // (column 0 holds NONE = 8 >> 4 = 0)
                     }
                 }
             }
@@ -871,7 +874,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                 const int k = mystage[l * kRowInts + ((v + tb.z) & (kRowInts - 1))];
                 __stcs(hp, k >> 4);
                 __stcs(hp + pdelta, k & 3);
-                if (!SWB_KMAX_IN_COMPUTE) mx = max(mx, k);
+                if (!SWB_KMAXC) mx = max(mx, k);
             }
         } else {
 #pragma unroll 2
@@ -886,7 +889,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
                     // column-strip mode: local column 0 belongs to the GPU on the left; its P holds the
                     // hand-off marker that ends this GPU's part of the backtrack
                     __stcs(hp + pdelta, (c == 0 && p.left_in != nullptr) ? kHandOff : (k & 3));
-                    if (!SWB_KMAX_IN_COMPUTE && c > 0) mx = max(mx, k);
+                    if (!SWB_KMAXC && c > 0) mx = max(mx, k);
                     // ... and my last column is the boundary column of the GPU on the right (P2P store over NVLink)
                     if (c == m && p.right_out != nullptr)
                         asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.right_out + r0 + kWRows * sub + l), "r"(k >> 4) : "memory");
@@ -913,7 +916,7 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
         if (lane == 0)
             asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p.right_flags + (r0 - 1) / kWRows + sub), "r"(p.epoch) : "memory");
     }
-    if (!SWB_KMAX_IN_COMPUTE) {
+    if (!SWB_KMAXC) {
         // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel)
         const int hm = __reduce_max_sync(0xffffffffu, mx) >> 4;
         if (lane == 0 && hm > 0) { atomicMax(p.strip_max + strip, hm); atomicMax(p.gmax, hm); }
@@ -1090,7 +1093,7 @@ fill_kernel(const FillParams p_in)
                       (unsigned)__cvta_generic_to_shared(s_drained + w * kWriters),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, strip + pair * p.nstrips);
-        if (STORE && SWB_KMAX_IN_COMPUTE) {
+        if (STORE && SWB_KMAXC) {
             // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel).  The rows past n of a
             // partial strip never match (inv), so their cells stay below the cells above them.
             const int mx = __reduce_max_sync(0xffffffffu, S.kmax) >> 4;
