@@ -79,13 +79,8 @@ constexpr int kStripRows = 32 * kR;    // rows per strip (compute warp)
 #endif
 constexpr int kWRows    = SWB_WRITER_ROWS;         // rows of a strip drained by one writer warp (8, 16 or 32)
 constexpr int kWriters  = kStripRows / kWRows;     // writer warps per strip
-// Experiment kept for the record: writers that unpack into shared memory and store with 128-byte TMA bulk copies
-// (one per row and matrix).  Measured 12.3 ms against 5.1 ms for the 45000x45000 fill: bulk copies this small
-// cost far more than the STGs they replace.  Off.
-#ifndef SWB_TMA_STORE
-#define SWB_TMA_STORE 0
-#endif
-constexpr int kTbufInts = 2 * 2 * kWRows * 32;     // per writer: double-buffered unpacked H and P rows of one round (16 KB)
+// (Tried and removed: writers that unpack into shared memory and store with 128-byte TMA bulk copies, one per row and
+// matrix -- 12.3 ms against 5.1 ms for the 45000x45000 fill: bulk copies this small cost far more than the STGs.)
 // KT (template parameter of the fill kernel) = staging ring depth in steps (16-byte slots per
 // row): 64 for single large pairs, 32 for batches of small pairs (more CTAs per SM)
 constexpr int kRing     = 64;          // hand-off ring capacity in blocks (power of two)
@@ -667,7 +662,7 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 template <int KT>
 __device__ __forceinline__ void writer_strip(const FillParams& p, const long long r0, const int sub, const int lane,
                                              const int* stage /* this strip: [32*kR][4*KT] */,
-                                             int4* rowtab, int* tbuf /* [2][2][kWRows][32] unpacked H / P rows for the bulk stores */,
+                                             int4* rowtab,
                                              volatile int* staged, volatile int* drained, const long long strip)
 {
     // strip row rho = 32*sub + lane is computed by compute lane cl = rho / kR.
@@ -692,8 +687,6 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
     const unsigned long long hbase = (unsigned long long)p.H + 4ull * (unsigned long long)(r0 * p.pitch - 1024);     // (E < 1024)
     if (lane < kWRows) rowoff[lane] = make_int2((int)(unsigned)(4 * (G0 - r0 * p.pitch + 1024)), F);
     const unsigned one = (unsigned)opaque(1);
-    const unsigned long long myrow_h = (unsigned long long)(p.H + G0);          // segment base of MY row (lane < kWRows)
-    (void)one; (void)myrow_h;
     const unsigned rowmask = __ballot_sync(0xffffffffu, myrow);
     const int nvalid = __popc(rowmask);
     const int Emax = __reduce_max_sync(0xffffffffu, myrow ? E : 0);
@@ -728,41 +721,6 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
         if (interior && nvalid == kWRows) {
         } else
 #endif
-#if SWB_TMA_STORE
-        if (interior && nvalid == kWRows) {
-            // (experiment, see SWB_TMA_STORE) Unpack the round into H and P rows in shared memory (lane = column:
-            // conflict-free) and let the TMA engine write them: lane l issues one 128-byte bulk copy per matrix for
-            // ITS row.  Motivation: the writers' STGs cost the compute warps speed (the fill runs 0.7 ms faster with
-            // the STGs removed and nothing else changed).
-            int* hb = tbuf + (r & 1) * (2 * kWRows * 32);
-            int* pb = hb + kWRows * 32;
-            // my bulk copies of round r-2 (same buffer) have read their source; then everybody's have
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-#pragma unroll 1
-            for (int l0 = 0; l0 < kWRows; l0 += 8) {
-                int k[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int2 tb = rowoff[l0 + i];
-                    k[i] = mystage[(l0 + i) * kRowInts + ((v + tb.y) & (kRowInts - 1))];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    hb[(l0 + i) * 32 + lane] = k[i] >> 4;
-                    pb[(l0 + i) * 32 + lane] = k[i] & 3;
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane < kWRows) {
-                const unsigned long long gh = myrow_h + 128ull * (unsigned)r;          // my row's segment of this round
-                const unsigned sh = (unsigned)__cvta_generic_to_shared(hb + lane * 32), sp = (unsigned)__cvta_generic_to_shared(pb + lane * 32);
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(gh), "r"(sh) : "memory");
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(gh + 4ull * (unsigned long long)pdelta), "r"(sp) : "memory");
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-#else
         if (interior && nvalid == kWRows) {
             // batches of 8 rows: all table and data loads first, then the 16 stores.  Per row the ALU pipe
             // sees the ring index (2 ops) and the unpacking (2 ops); the two addresses are one IMAD.WIDE each
@@ -839,7 +797,6 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #endif
             }
 #endif
-#endif
         } else if (KT == 32 && p.left_in == nullptr && p.right_out == nullptr) {
             // Edge rounds (for some rows part of the round lies left of column 0 or right of column m) and the partial
             // last strip of a pair: batches of 8 rows with predicated stores.  For small matrices most rounds are edge
@@ -906,9 +863,6 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #ifdef SWB_X_WRITERTRACE
     if (p.trace && lane == 0 && sub == 0) { p.trace[strip * 8 + 5] = dw_wait; p.trace[strip * 8 + 6] = dw_work; p.trace[strip * 8 + 7] = dw_n; }
 #endif
-#if SWB_TMA_STORE
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                   // my bulk stores are complete
-#endif
     if (p.right_flags != nullptr && nvalid > 0) {
         // column-strip mode: every lane's boundary stores are ordered before the flag the right GPU polls
         __threadfence_system();
@@ -963,8 +917,7 @@ __host__ __device__ constexpr int fill_block_threads(int wpc, bool store)
 }
 __host__ __device__ constexpr size_t fill_smem_bytes(int wpc, int KT, bool store)
 {
-    return (size_t)wpc * ((store ? (size_t)kStripRows * 4 * KT * sizeof(int) + kWriters * 48 * sizeof(int4) +
-                                   (SWB_TMA_STORE ? kWriters * (size_t)kTbufInts * sizeof(int) : 0) : 0) +
+    return (size_t)wpc * ((store ? (size_t)kStripRows * 4 * KT * sizeof(int) + kWriters * 48 * sizeof(int4) : 0) +
                           kRing * sizeof(int4));
 }
 
@@ -1010,8 +963,7 @@ fill_kernel(const FillParams p_in)
 
     int4* stage4  = smem4;                                       // [wpc][kStripRows][KT]   (STORE only)
     int4* rings   = stage4 + (STORE ? (size_t)wpc * kStripRows * KT : 0);   // [wpc][kRing]
-    int*  tbufs   = reinterpret_cast<int*>(rings + (size_t)wpc * kRing);      // [wpc*kWriters][kTbufInts] (STORE, bulk stores)
-    int4* rowtabs = reinterpret_cast<int4*>(tbufs + ((STORE && SWB_TMA_STORE) ? (size_t)wpc * kWriters * kTbufInts : 0));   // [wpc*kWriters][48] (STORE only)
+    int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc*kWriters][48]      (STORE only)
 
     for (int i = threadIdx.x; i < wpc * kRing; i += blockDim.x) rings[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
@@ -1119,7 +1071,7 @@ fill_kernel(const FillParams p_in)
         const long long r0 = band_r0 + (long long)kStripRows * cw;
         if (r0 > p.n) return;                                    // (a writer without valid rows still runs: it owns a drained flag)
         writer_strip<KT>(p, r0, sub, lane, reinterpret_cast<const int*>(stage4 + (size_t)cw * kStripRows * KT),
-                     rowtabs + (size_t)wi * 48, tbufs + (size_t)wi * kTbufInts, s_staged + cw, s_drained + wi,
+                     rowtabs + (size_t)wi * 48, s_staged + cw, s_drained + wi,
                      (r0 - 1) / kStripRows);
     } else if (role == 2) {
         // ------------------------------------------------ loader
