@@ -19,7 +19,8 @@
 //    every row they read 32 consecutive columns (conflict-free LDS.32), unpack H and P and
 //    store them with two warp-wide stores that each cover ONE FULL 128-byte line of the
 //    caller's row-major matrix (the segmentation is chosen per row so that this holds for
-//    any pitch).  The writers also keep the strip maximum for maxPos.
+//    any pitch; a half-warp per row with 8-byte stores in the steady rounds).  The strip maximum
+//    for maxPos is kept by the writers (single pair) or the compute warp (batch, score only).
 //  * Strip -> strip hand-off (last row of a strip feeds the first row of the next): lane
 //    31 stores its H block into a 64-entry shared-memory ring of the next compute warp of
 //    the CTA ("band" = wpc strips); the entry carries an epoch tag in its low bits, so the
@@ -31,7 +32,15 @@
 //  * A compute warp never diverges: every poll is executed by all 32 lanes on a broadcast
 //    address and hand-off stores are PTX-predicated.  (A lane-0-only spin loop leaves the
 //    warp split and every following shuffle takes the divergent slow path: measured 8x
-//    slower steps.)
+//    slower steps.)  It polls the strip above once per RUN of 4 or 8 steps, for the last block
+//    the run needs, and executes the run without a branch (a tag check per step cost a third of
+//    the step: the branch kept ptxas from overlapping consecutive steps); its waits never sleep
+//    (__nanosleep oversleeps by microseconds and put whole launches into a slow mode).
+//  * The edges of the matrix need no special code in the common case: the packed copy of a is
+//    padded with the byte 0, which matches nothing unless b holds a NUL byte (the prep kernel
+//    checks), so column 0, the blocks of lanes that have not started yet and the columns past m
+//    evaluate to H = 0 / harmless values by themselves; a forced variant of the step covers the
+//    NUL case, the column-strip mode (one pair on several GPUs) and the score-only tail.
 //  * maxPos: a second tiny kernel scans only the strips that attain the global maximum,
 //    with the reference's tie-break (first in anti-diagonal order, bottom-left to
 //    top-right; omp_smithW.c:203-215,384-387).
