@@ -43,7 +43,8 @@ typedef enum {
     SWB_ERR_ALIGN     = -2,   /* dH/dP not 16-byte aligned                                 */
     SWB_ERR_CUDA      = -3,   /* a CUDA call failed (see swb_last_cuda_error)              */
     SWB_ERR_RANGE     = -4,   /* sizes/scores outside what 32-bit packed scores can hold   */
-    SWB_ERR_NOMEM     = -5    /* device or pinned-host allocation failed                   */
+    SWB_ERR_NOMEM     = -5,   /* device or pinned-host allocation failed                   */
+    SWB_ERR_IO        = -6    /* sequence file / manifest unreadable or malformed          */
 } swb_status;
 
 /* omp_smithW.c:75-77 (matchScore, missmatchScore, gapScore); NULL means 3,-3,-2 */
@@ -56,10 +57,10 @@ typedef struct { int32_t match, mismatch, gap; } swb_scoring;
 /* Tuning knobs (0 = library default).  Not part of the reference surface. */
 typedef struct swb_timer swb_timer;   /* CUDA-event pair around the fill kernel only */
 typedef struct {
-    int32_t warps_per_band;   /* compute warps (32-row strips) per CTA band, 1..4   */
+    int32_t warps_per_band;   /* compute warps (64-row strips) per CTA band, 1..2 (larger values are clamped to 2) */
     int32_t reserved[5];
     swb_timer* timer;         /* if set, swb_fill_async brackets the fill kernel launch with its events */
-    uint64_t* trace;          /* developer tool: DEVICE buffer of ceil(n/32)*8 uint64 globaltimer stamps per strip, or NULL */
+    uint64_t* trace;          /* developer tool: DEVICE buffer of ceil(n/64)*8 uint64 globaltimer stamps (8 per 64-row strip), or NULL; honoured by the -DSWB_TRACE developer build only */
 } swb_tuning;
 
 /* Kernel-only timing for the roofline figure: events are recorded on the call's stream
@@ -146,6 +147,24 @@ int swb_fill_batch_async(const char* a, int64_t m, const char* b, int64_t n, int
                          const swb_scoring* scoring, int32_t* dH, int32_t* dP, int64_t pitch, int64_t pair_stride,
                          int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream, const swb_tuning* tuning);
 
+/* Batch of independent pairs of ANY shapes (SURVEY 8(b) swb_fill_batch with per-pair m[], n[]; the reference
+ * runs one pair per process).  HOST arrays of npairs entries: a_off / b_off = byte offset of pair k's sequences in
+ * a / b (host or device concatenations), m / n = its lengths, hp_off = int32 offset of its matrices in dH / dP (a
+ * multiple of 4; the matrices have the single-pair layout with pitch m[k]+1).  Runs of consecutive pairs with the
+ * same shape, packed sequences and a uniform matrix stride go out as ONE batched launch (the 65536 x 256x256
+ * configuration is a single run); other pairs get a launch each.  d_maxPos / d_maxScore: DEVICE arrays of npairs
+ * entries (maxPos relative to the pair's own matrix) or NULL. */
+int swb_fill_pairs_async(const char* a, const int64_t* a_off, const int64_t* m,
+                         const char* b, const int64_t* b_off, const int64_t* n,
+                         const int64_t* hp_off, int64_t npairs, const swb_scoring* scoring,
+                         int32_t* dH, int32_t* dP, int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream);
+
+/* Pair-wise sharding of a batch over the GPUs of a box (BASELINE config "batch of 65536 independent 256x256 pairs
+ * ... sharded pair-wise across 8 B200"; SURVEY 8(e): contiguous blocks, no exchange): shard `shard` of `nshards`
+ * owns pairs first .. first+count-1.  Every GPU then calls swb_fill_batch_async / swb_fill_pairs_async on its own
+ * pairs; nothing crosses the GPUs. */
+int swb_shard_pairs(int64_t npairs, int nshards, int shard, int64_t* first, int64_t* count);
+
 /* ---- column-strip mode: ONE pair across several GPUs (BASELINE config "100000x100000 single pair,
  * column-strip wavefront pipelined across 2/4/8 B200 with NVLink P2P boundary exchange").
  * The reference has no multi-GPU form; this extends the nDiag wavefront (omp_smithW.c:203-216).
@@ -178,6 +197,33 @@ int64_t swb_strip_flag_count(int64_t n);
 int swb_backtrack_from_async(int32_t* dP, int64_t pitch, int64_t startPos, int64_t* d_pathLen, int64_t* d_endPos,
                              int device, void* stream);
 
+/* ---- C++ host driver for the column-strip mode inside ONE process (SURVEY 8(b) swb_fill_multi): the pair is
+ * split into ndev contiguous column blocks, strip g on devices[g] (devices may repeat: such strips share a stream
+ * and run left to right), peer access is enabled between neighbours, every strip has its own stream and all fill
+ * kernels run concurrently, linked only by the NVLink boundary stores of swb_fill_strip_async.  maxPos is reduced
+ * on the host from one (score, position) pair per GPU with the reference's tie-break (omp_smithW.c:384-387) and
+ * the backtrack (omp_smithW.c:405-420) walks right to left over the strips.  a, b: HOST sequences of the whole pair.
+ * maxPos indexes the (n+1) x (m+1) matrix of the whole pair.  swb_multi_gather_host copies the strips into the
+ * reference's row-major host layout (pitch m+1; either pointer may be NULL); swb_multi_strip exposes one strip's
+ * device slab (local column j = global column col0 + j; local column 0 of strips g > 0 holds the left
+ * neighbour's last column in H and the hand-off marker 5 in P). */
+typedef struct swb_multi swb_multi;
+int  swb_multi_create(swb_multi** out, int64_t m, int64_t n, const int* devices, int ndev);
+int  swb_multi_fill(swb_multi* h, const char* a, const char* b, const swb_scoring* scoring,
+                    int64_t* maxPos, int32_t* maxScore);
+int  swb_multi_backtrack(swb_multi* h, int64_t maxPos, int64_t* path_len);
+int  swb_multi_align(swb_multi* h, const char* a, const char* b, const swb_scoring* scoring,
+                     int64_t* maxPos, int32_t* maxScore, int64_t* path_len, int do_backtrack);  /* = fill [+ backtrack] */
+int  swb_multi_strips(const swb_multi* h);
+int  swb_multi_strip(const swb_multi* h, int g, int* device, int64_t* col0, int64_t* m_local, int64_t* pitch,
+                     int32_t** dH, int32_t** dP);
+int  swb_multi_gather_host(swb_multi* h, int32_t* H, int32_t* P);
+void swb_multi_destroy(swb_multi* h);
+/* one-shot form: create, align, gather (H, P: HOST (n+1) x (m+1) int32 or NULL), destroy */
+int  swb_fill_multi(const char* a, int64_t m, const char* b, int64_t n, const swb_scoring* scoring,
+                    const int* devices, int ndev, int32_t* H, int32_t* P,
+                    int64_t* maxPos, int64_t* path_len, int do_backtrack);
+
 /* Boundary buffers that another process maps (cudaMalloc + CUDA IPC): allocation (zero-filled),
  * 64-byte IPC handle, mapping a peer's handle on `device`, and peer access between two devices of
  * one process. */
@@ -187,6 +233,21 @@ int   swb_ipc_get_handle(void* p, unsigned char* out64);
 int   swb_ipc_open(const unsigned char* handle64, int device, void** out);
 int   swb_ipc_close(void* p, int device);
 int   swb_enable_peer(int device, int peer);
+
+/* ---- real sequence input, host only: replaces generate() (omp_smithW.c:489-519) as the source of
+ * a and b.  Files are FASTA ('>' headers; letters are upper-cased, white space dropped; a file without a header
+ * is one anonymous record) or UCSC .2bit (detected by its signature; N blocks come back as 'N').  swb_seq_read
+ * returns record `record` (0-based) as a malloc'ed, NUL-terminated string (free with swb_seq_free); name may be NULL.
+ * A manifest is a text file with one pair per line, "<fileA>[:record] <fileB>[:record]" ('#' comments, paths
+ * relative to the manifest): the pairs of a variable-length batch for swb_fill_pairs_async. */
+int  swb_seq_count(const char* path, int64_t* nrecords);
+int  swb_seq_read(const char* path, int64_t record, char** seq, int64_t* len, char* name, size_t name_cap);
+void swb_seq_free(char* seq);
+typedef struct swb_manifest swb_manifest;
+int     swb_manifest_load(const char* path, swb_manifest** out);
+int64_t swb_manifest_pairs(const swb_manifest* m);
+int     swb_manifest_pair(const swb_manifest* m, int64_t k, const char** a, int64_t* alen, const char** b, int64_t* blen);
+void    swb_manifest_free(swb_manifest* m);
 
 /* The reference's generate() (omp_smithW.c:489-519): srand(seed) then m+1 draws
  * for a and n+1 draws for b with this libc's rand(), 0->A 2->C 3->G else T.

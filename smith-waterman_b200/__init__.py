@@ -19,7 +19,8 @@ from pathlib import Path
 
 __all__ = ["lib", "SwbError", "Scoring", "DEFAULT_SCORING", "generate", "fill", "fill_async", "fill_batch_async", "score_only_async", "backtrack", "backtrack_async",
            "smithWaterman", "align_host", "AlignContext", "score_only", "KernelTimer", "host_alloc", "host_free",
-           "device_count", "LIB_PATH", "NONE", "UP", "LEFT", "DIAGONAL", "PATH"]
+           "device_count", "LIB_PATH", "NONE", "UP", "LEFT", "DIAGONAL", "PATH",
+           "fill_pairs_async", "shard_pairs", "MultiGpuPair", "read_sequences", "read_sequence", "load_manifest"]
 
 # omp_smithW.c:32-36
 PATH, NONE, UP, LEFT, DIAGONAL = -1, 0, 1, 2, 3
@@ -86,6 +87,31 @@ def _load() -> C.CDLL:
     L.swb_timer_destroy.argtypes = [vp]; L.swb_timer_destroy.restype = None
     L.swb_host_alloc.argtypes = [C.c_size_t]; L.swb_host_alloc.restype = vp
     L.swb_host_free.argtypes = [vp]; L.swb_host_free.restype = None
+    pi64 = C.POINTER(i64)
+    L.swb_fill_pairs_async.argtypes = [vp, pi64, pi64, vp, pi64, pi64, pi64, i64, C.POINTER(Scoring), vp, vp, vp, vp,
+                                       C.c_int, vp]
+    L.swb_shard_pairs.argtypes = [i64, C.c_int, C.c_int, pi64, pi64]
+    L.swb_multi_create.argtypes = [C.POINTER(vp), i64, i64, C.POINTER(C.c_int), C.c_int]
+    L.swb_multi_fill.argtypes = [vp, vp, vp, C.POINTER(Scoring), pi64, C.POINTER(i32)]
+    L.swb_multi_backtrack.argtypes = [vp, i64, pi64]
+    L.swb_multi_align.argtypes = [vp, vp, vp, C.POINTER(Scoring), pi64, C.POINTER(i32), pi64, C.c_int]
+    L.swb_multi_strips.argtypes = [vp]
+    L.swb_multi_strip.argtypes = [vp, C.c_int, C.POINTER(C.c_int), pi64, pi64, pi64, C.POINTER(vp), C.POINTER(vp)]
+    L.swb_multi_gather_host.argtypes = [vp, vp, vp]
+    L.swb_multi_destroy.argtypes = [vp]; L.swb_multi_destroy.restype = None
+    L.swb_fill_multi.argtypes = [vp, i64, vp, i64, C.POINTER(Scoring), C.POINTER(C.c_int), C.c_int, vp, vp, pi64, pi64,
+                                 C.c_int]
+    L.swb_seq_count.argtypes = [C.c_char_p, pi64]
+    L.swb_seq_read.argtypes = [C.c_char_p, i64, C.POINTER(vp), pi64, C.c_char_p, C.c_size_t]
+    L.swb_seq_free.argtypes = [vp]; L.swb_seq_free.restype = None
+    L.swb_manifest_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.swb_manifest_pairs.argtypes = [vp]; L.swb_manifest_pairs.restype = i64
+    L.swb_manifest_pair.argtypes = [vp, i64, C.POINTER(vp), pi64, C.POINTER(vp), pi64]
+    L.swb_manifest_free.argtypes = [vp]; L.swb_manifest_free.restype = None
+    for name in ("swb_fill_pairs_async", "swb_shard_pairs", "swb_multi_create", "swb_multi_fill", "swb_multi_backtrack",
+                 "swb_multi_align", "swb_multi_strips", "swb_multi_strip", "swb_multi_gather_host", "swb_fill_multi",
+                 "swb_seq_count", "swb_seq_read", "swb_manifest_load", "swb_manifest_pair"):
+        getattr(L, name).restype = C.c_int
     for name in ("swb_fill_async", "swb_fill", "swb_backtrack_async", "swb_backtrack", "swb_align_host",
                  "swb_ctx_create", "swb_ctx_align", "swb_score_only", "swb_score_only_async", "swb_fill_batch_async",
                  "swb_fill_strip_async", "swb_backtrack_from_async", "swb_ipc_get_handle", "swb_ipc_open", "swb_ipc_close",
@@ -294,3 +320,106 @@ def host_alloc(nbytes: int) -> int:
 
 def host_free(p: int) -> None:
     lib.swb_host_free(p)
+
+
+# ---------------------------------------------------------------------------------------------
+# variable-length batches, pair-wise sharding (SURVEY 8(b) swb_fill_batch with m[], n[]; 8(e))
+# ---------------------------------------------------------------------------------------------
+def _i64_array(xs):
+    return (C.c_int64 * len(xs))(*[int(x) for x in xs])
+
+
+def fill_pairs_async(a, a_off, m, b, b_off, n, hp_off, dH, dP, d_maxPos=None, d_maxScore=None, scoring=None,
+                     device: int = 0, stream=None) -> None:
+    """Enqueue the fill of len(m) independent pairs of any shapes (swb_fill_pairs_async): a, b are host or
+    device concatenations, a_off / b_off / hp_off / m / n host sequences of ints."""
+    sc = _scoring(scoring)
+    _check(lib.swb_fill_pairs_async(_ptr(a), _i64_array(a_off), _i64_array(m), _ptr(b), _i64_array(b_off), _i64_array(n),
+                                    _i64_array(hp_off), len(m), C.byref(sc), _ptr(dH), _ptr(dP), _ptr(d_maxPos),
+                                    _ptr(d_maxScore), device, _stream_ptr(stream)))
+
+
+def shard_pairs(npairs: int, nshards: int, shard: int):
+    """-> (first, count): the contiguous block of pairs GPU `shard` of `nshards` owns (swb_shard_pairs)."""
+    first, count = C.c_int64(0), C.c_int64(0)
+    _check(lib.swb_shard_pairs(npairs, nshards, shard, C.byref(first), C.byref(count)))
+    return int(first.value), int(count.value)
+
+
+class MultiGpuPair:
+    """ONE pair in column strips over several GPUs of this process (swb_multi_*: the C++ host driver)."""
+
+    def __init__(self, m: int, n: int, devices):
+        self.m, self.n, self.devices = m, n, list(devices)
+        self._h = C.c_void_p(0)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        _check(lib.swb_multi_create(C.byref(self._h), m, n, arr, len(self.devices)))
+
+    def fill(self, a: bytes, b: bytes, scoring=None):
+        """-> (maxPos, maxScore); maxPos indexes the (n+1) x (m+1) matrix of the whole pair"""
+        sc = _scoring(scoring)
+        pos, score = C.c_int64(0), C.c_int32(0)
+        _check(lib.swb_multi_fill(self._h, _ptr(a), _ptr(b), C.byref(sc), C.byref(pos), C.byref(score)))
+        return int(pos.value), int(score.value)
+
+    def backtrack(self, maxPos: int) -> int:
+        plen = C.c_int64(0)
+        _check(lib.swb_multi_backtrack(self._h, maxPos, C.byref(plen)))
+        return int(plen.value)
+
+    def strip(self, g: int):
+        """-> dict(device, col0, m, pitch, dH, dP) of strip g (dH, dP raw device addresses)"""
+        dev = C.c_int(0); col0, ml, pitch = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        dH, dP = C.c_void_p(0), C.c_void_p(0)
+        _check(lib.swb_multi_strip(self._h, g, C.byref(dev), C.byref(col0), C.byref(ml), C.byref(pitch), C.byref(dH), C.byref(dP)))
+        return dict(device=dev.value, col0=col0.value, m=ml.value, pitch=pitch.value, dH=dH.value, dP=dP.value)
+
+    def gather_host(self, H=None, P=None) -> None:
+        """copies the strips into host (n+1) x (m+1) int32 matrices (numpy / pinned); either may be None"""
+        _check(lib.swb_multi_gather_host(self._h, _ptr(H), _ptr(P)))
+
+    def close(self) -> None:
+        if self._h:
+            lib.swb_multi_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# real sequence input (SURVEY 8(f)2): FASTA / UCSC .2bit files and batch manifests
+# ---------------------------------------------------------------------------------------------
+def read_sequence(path, record: int = 0):
+    """-> (name, sequence bytes) of one record of a FASTA / .2bit file (swb_seq_read)"""
+    seq, ln = C.c_void_p(0), C.c_int64(0)
+    name = C.create_string_buffer(256)
+    _check(lib.swb_seq_read(str(path).encode(), record, C.byref(seq), C.byref(ln), name, 256))
+    try:
+        return name.value.decode(), C.string_at(seq.value, ln.value)
+    finally:
+        lib.swb_seq_free(seq)
+
+
+def read_sequences(path):
+    cnt = C.c_int64(0)
+    _check(lib.swb_seq_count(str(path).encode(), C.byref(cnt)))
+    return [read_sequence(path, k) for k in range(cnt.value)]
+
+
+def load_manifest(path):
+    """-> [(a bytes, b bytes)] of a batch manifest (swb_manifest_load)"""
+    h = C.c_void_p(0)
+    _check(lib.swb_manifest_load(str(path).encode(), C.byref(h)))
+    try:
+        out = []
+        for k in range(lib.swb_manifest_pairs(h)):
+            pa, pb, la, lb = C.c_void_p(0), C.c_void_p(0), C.c_int64(0), C.c_int64(0)
+            _check(lib.swb_manifest_pair(h, k, C.byref(pa), C.byref(la), C.byref(pb), C.byref(lb)))
+            out.append((C.string_at(pa.value, la.value), C.string_at(pb.value, lb.value)))
+        return out
+    finally:
+        lib.swb_manifest_free(h)

@@ -73,6 +73,7 @@ struct Workspace {
     int* strip_max = nullptr;
     int4* boundary = nullptr; long long bstride = 0;
     unsigned long long* row_best = nullptr;
+    int4* prof = nullptr; long long prof_stride = 0, prof_pair_stride = 0;
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -105,16 +106,26 @@ int pick_wpc(int64_t n, int64_t npairs, int kt, bool store, const swb_tuning* tu
     return wpc;
 }
 
-template <int KT, bool STORE>
-cudaError_t launch_fill(const swb::FillParams& p, long long nblocks, int wpc, cudaStream_t st)
+template <int KT, bool STORE, bool PROF>
+cudaError_t launch_fill_one(const swb::FillParams& p, long long nblocks, int wpc, cudaStream_t st)
 {
     // score-only needs 1 KB per strip but asks for the full-fill footprint of a large pair: one CTA per SM
     // keeps waiting CTAs off the schedulers of the working ones (measured 13 ms -> see DESIGN.md)
     const size_t smem = (!STORE && p.nbands > 8) ? swb::fill_smem_bytes(wpc, 64, true) : swb::fill_smem_bytes(wpc, KT, STORE);
-    cudaError_t e = cudaFuncSetAttribute(swb::fill_kernel<KT, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(swb::fill_kernel<KT, STORE, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    swb::fill_kernel<KT, STORE><<<(unsigned)nblocks, swb::fill_block_threads(wpc, STORE), smem, st>>>(p);
+    swb::fill_kernel<KT, STORE, PROF><<<(unsigned)nblocks, swb::fill_block_threads(wpc, STORE), smem, st>>>(p);
     return cudaGetLastError();
+}
+
+// Both instantiations are enqueued: the one that does not match the alphabet of b (counted on the device, so that the
+// call stays asynchronous for device-resident sequences) returns at once.
+template <int KT, bool STORE>
+cudaError_t launch_fill(const swb::FillParams& p, long long nblocks, int wpc, cudaStream_t st)
+{
+    cudaError_t e = launch_fill_one<KT, STORE, true>(p, nblocks, wpc, st);
+    if (e != cudaSuccess) return e;
+    return launch_fill_one<KT, STORE, false>(p, nblocks, wpc, st);
 }
 
 // The one implementation behind swb_fill_async, swb_fill_batch_async and swb_score_only_async.
@@ -164,7 +175,10 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
     const size_t o_a4 = carve((size_t)npairs * ws.a4_words * sizeof(unsigned));
     const size_t o_a = carve(a_on_dev ? 0 : (size_t)(m * npairs));
     const size_t o_b = carve(b_on_dev ? 0 : (size_t)(n * npairs));
-    const size_t o_small = carve(256);
+    const size_t o_small = carve(2048);           // ticket, NUL flag, letter count | present[256] | lmap[256]
+    ws.prof_stride = swb::kProfPad + (long long)ngroups * swb::kGroup + 16;
+    ws.prof_pair_stride = ws.prof_stride * swb::kProfRows;
+    const size_t o_prof = carve((size_t)npairs * (size_t)ws.prof_pair_stride * sizeof(int4));
     const size_t o_gmax = carve((size_t)npairs * sizeof(int));
     const size_t o_key = carve((size_t)npairs * sizeof(unsigned long long));
     const size_t o_smax = carve((size_t)(strips * npairs) * sizeof(int));
@@ -180,6 +194,10 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
     ws.strip_max = reinterpret_cast<int*>(ws.base + o_smax);
     ws.boundary = reinterpret_cast<int4*>(ws.base + o_bnd);
     ws.row_best = reinterpret_cast<unsigned long long*>(ws.base + o_rb);
+    ws.prof = reinterpret_cast<int4*>(ws.base + o_prof);
+    int* const d_nletters = ws.ticket + 2;
+    int* const d_present = ws.ticket + 64;
+    unsigned char* const d_lmap = reinterpret_cast<unsigned char*>(ws.ticket + 64 + 256);
 
     int rc = SWB_OK;
     auto run = [&]() -> int {
@@ -199,12 +217,20 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
         }
         // band-boundary rows carry their validity tag in the data: clear the tags
         if (boundary_bytes) SWB_CUDA(cudaMemsetAsync(ws.boundary, 0, boundary_bytes, st));
-        SWB_CUDA(cudaMemsetAsync(ws.ticket, 0, 256, st));            // ticket, NUL flag
+        SWB_CUDA(cudaMemsetAsync(ws.ticket, 0, 2048, st));           // ticket, NUL flag, alphabet of b
         const int prep_blocks = (int)std::min<int64_t>((ws.a4_words * npairs + 255) / 256, 1184);
         swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, npairs, ws.a4, ws.a4_words, ws.ticket, ws.gmax, ws.key,
                                                       ws.strip_max, (long long)(strips * npairs), b_d, (long long)(n * npairs),
-                                                      ws.ticket + 1);
+                                                      ws.ticket + 1, d_present);
         SWB_CUDA(cudaGetLastError());
+        {
+            const int64_t items = ws.prof_pair_stride * npairs;
+            const int pblocks = (int)std::min<int64_t>((items + 255) / 256, 1184);
+            swb::profile_kernel<<<pblocks, 256, 0, st>>>(a_d, m, npairs, d_present, d_lmap, d_nletters, ws.prof, ws.prof_stride,
+                                                         ws.prof_pair_stride, 16 * sc.match + swb::kTieDiag,
+                                                         16 * sc.mismatch + swb::kTieDiag);
+            SWB_CUDA(cudaGetLastError());
+        }
 
         swb::FillParams p{};
         p.a4 = ws.a4; p.b = b_d;
@@ -219,6 +245,8 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
         p.trace = tuning ? reinterpret_cast<unsigned long long*>(tuning->trace) : nullptr;
         p.nbands = nbands; p.nstrips = strips; p.a4_stride = ws.a4_words; p.pair_stride = pair_stride;
         p.row_best = ws.row_best;
+        p.prof = ws.prof; p.prof_stride = ws.prof_stride; p.prof_pair_stride = ws.prof_pair_stride;
+        p.lmap = d_lmap; p.nletters = d_nletters;
         if (link) { p.left_in = link->left_in; p.left_flags = link->left_flags; p.right_out = link->right_out;
                     p.right_flags = link->right_flags; p.epoch = link->epoch; }
         swb_timer* timer = tuning ? tuning->timer : nullptr;
@@ -265,6 +293,7 @@ const char* swb_strerror(int status)
     case SWB_ERR_CUDA:  return "CUDA error (see swb_last_cuda_error)";
     case SWB_ERR_RANGE: return "sizes or scores exceed the 32-bit packed score range";
     case SWB_ERR_NOMEM: return "out of device or pinned host memory";
+    case SWB_ERR_IO:    return "sequence file or manifest unreadable or malformed";
     default:            return "unknown swb status";
     }
 }
@@ -345,6 +374,40 @@ int swb_fill_batch_async(const char* a, int64_t m, const char* b, int64_t n, int
 {
     return fill_impl(a, m, b, n, npairs, scoring, dH, dP, pitch, pair_stride, d_maxPos, d_maxScore, device, stream,
                      tuning, true);
+}
+
+int swb_fill_pairs_async(const char* a, const int64_t* a_off, const int64_t* m,
+                         const char* b, const int64_t* b_off, const int64_t* n,
+                         const int64_t* hp_off, int64_t npairs, const swb_scoring* scoring,
+                         int32_t* dH, int32_t* dP, int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream)
+{
+    if (!a || !a_off || !m || !b || !b_off || !n || !hp_off || npairs <= 0 || !dH || !dP) return SWB_ERR_ARG;
+    int64_t k = 0;
+    while (k < npairs) {
+        // the longest run of equally shaped pairs with packed sequences and a uniform matrix stride
+        int64_t run = 1, stride = 0;
+        if (k + 1 < npairs) stride = hp_off[k + 1] - hp_off[k];
+        while (k + run < npairs && m[k + run] == m[k] && n[k + run] == n[k] &&
+               a_off[k + run] - a_off[k + run - 1] == m[k] && b_off[k + run] - b_off[k + run - 1] == n[k] &&
+               hp_off[k + run] - hp_off[k + run - 1] == stride && stride >= (n[k] + 1) * (m[k] + 1))
+            ++run;
+        if (hp_off[k] & 3) return SWB_ERR_ALIGN;
+        const int rc = fill_impl(a + a_off[k], m[k], b + b_off[k], n[k], run, scoring, dH + hp_off[k], dP + hp_off[k],
+                                 m[k] + 1, run > 1 ? stride : 0, d_maxPos ? d_maxPos + k : nullptr,
+                                 d_maxScore ? d_maxScore + k : nullptr, device, stream, nullptr, true);
+        if (rc != SWB_OK) return rc;
+        k += run;
+    }
+    return SWB_OK;
+}
+
+int swb_shard_pairs(int64_t npairs, int nshards, int shard, int64_t* first, int64_t* count)
+{
+    if (npairs < 0 || nshards < 1 || shard < 0 || shard >= nshards || !first || !count) return SWB_ERR_ARG;
+    const int64_t base = npairs / nshards, rem = npairs % nshards;
+    *first = base * shard + std::min<int64_t>(shard, rem);
+    *count = base + (shard < rem ? 1 : 0);
+    return SWB_OK;
 }
 
 int swb_fill_strip_async(const char* a_local, int64_t m_local, const char* b, int64_t n,

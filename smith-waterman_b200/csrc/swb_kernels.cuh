@@ -102,6 +102,17 @@ constexpr int kWaitSteps = SWB_WAIT_STEPS;   // steps per poll of the strip abov
 #define SWB_WAIT_STEPS_SINGLE 8        // measured: 45000x45000 4.99 -> 4.89 ms, 100000x100000 18.7 -> 18.5 ms; the batch and
 #endif                                 // score-only instantiations are 2 % faster with 4
 constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
+// Score profile (PROF instantiations): when b uses at most kMaxLetters distinct byte values, the substitution scores
+// come from a table prof[letter][block] = the four keys 16*s + kTieDiag of columns 4j..4j+3 against that letter
+// (one 16-byte load per row and step, prefetched kProfDepth steps ahead) instead of being derived from the packed
+// characters with a compare and a select per cell on the compute warp's ALU pipe.  Row kMaxLetters of the table
+// never matches (rows past n of a partial strip).
+constexpr int kMaxLetters = 8;
+constexpr int kProfRows   = kMaxLetters + 1;
+constexpr int kProfPad    = 32;        // leading pad blocks of a profile row (blocks -31..-1 of a strip's first steps)
+// prefetch distance in steps (power of two, <= kGroup): 4 in the single-pair full fill (one CTA per SM, registers to
+// spare), 2 in the batch and score-only instantiations (two CTAs per SM: 80 registers)
+__host__ __device__ constexpr int prof_depth(int KT, bool STORE) { return (KT == 64 && STORE) ? 4 : 2; }
 constexpr int kBoundaryPad = 32;       // spare blocks in front of a band-boundary row (blocks -31..-1 of a strip's first steps)
 constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: compute warps on schedulers 0..wpc-1,
                                        // writers + loader on the others
@@ -138,6 +149,13 @@ struct FillParams {
     long long       bstride;
     int*            ticket;                // band ticket counter
     const int*      nul_flag;              // != 0: b holds a NUL byte (it would match the zero padding of a: see prep_kernel)
+    // score profile (see kMaxLetters): pair k uses prof + k*prof_pair_stride; the table and the letter map are
+    // shared by all pairs of a batch only through their layout, not their contents
+    const int4*     prof;                  // [kProfRows][prof_stride] per pair
+    long long       prof_stride, prof_pair_stride;
+    const unsigned char* lmap;             // [256] byte value -> profile row (letters of b over ALL pairs)
+    const int*      nletters;              // distinct byte values in b; > kMaxLetters: the PROF instantiation returns at once,
+                                           // <= kMaxLetters: the character-compare instantiation does
     int*            strip_max;             // [nstrips] max H of each strip (atomicMax by its writers)
     int*            gmax;                  // global max H
     unsigned long long* trace;             // optional [nstrips][8] globaltimer stamps (developer tool) or nullptr
@@ -279,7 +297,7 @@ __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m, lo
                             unsigned* __restrict__ a4, long long nwords,
                             int* ticket, int* gmax, unsigned long long* key,
                             int* strip_max, long long nstrips_total,
-                            const unsigned char* __restrict__ b, long long nb, int* nul_flag)
+                            const unsigned char* __restrict__ b, long long nb, int* nul_flag, int* present)
 {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
@@ -302,7 +320,11 @@ __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m, lo
     // neighbours by themselves: the compute warp runs the same code on every step of a strip.
     {
         bool nul = false;
-        for (long long k = tid; k < nb; k += nth) nul |= (b[k] == 0);
+        for (long long k = tid; k < nb; k += nth) {
+            const unsigned c = b[k];
+            nul |= (c == 0);
+            if (present[c] == 0) present[c] = 1;       // alphabet of b (benign race: every writer stores 1)
+        }
         if (nul) *nul_flag = 1;
     }
     for (long long k = tid; k < nstrips_total; k += nth) strip_max[k] = 0;
@@ -311,9 +333,63 @@ __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m, lo
 }
 
 // ---------------------------------------------------------------------------------
+// score profile (matchMissmatchScore, omp_smithW.c:394-399, tabulated per letter of b): every block first ranks
+// the byte values that occur in b (present[], set by prep_kernel); block 0 publishes the map and the count.  With
+// at most kMaxLetters letters, row r of the table holds for every block j the keys 16*s + kTieDiag of columns
+// 4j..4j+3 (column c reads a[c-1]) against letter r; positions outside the sequence and the row kMaxLetters
+// never match.
+// ---------------------------------------------------------------------------------
+__global__ void profile_kernel(const unsigned char* __restrict__ a, long long m, long long npairs,
+                               const int* __restrict__ present, unsigned char* lmap, int* nletters,
+                               int4* __restrict__ prof, long long prof_stride, long long prof_pair_stride,
+                               int s_match, int s_mismatch)
+{
+    __shared__ unsigned char s_letter[kProfRows];
+    __shared__ int s_cnt[8];
+    __shared__ int s_n;
+    {
+        // rank of byte value c among the present ones (256 threads = one per value)
+        const int c = threadIdx.x;
+        const bool on = c < 256 && present[c] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if ((c & 31) == 0 && c < 256) s_cnt[c >> 5] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 8; ++w) { if (w < (c >> 5)) before += s_cnt[w]; total += s_cnt[w]; }
+        const int rank = before + __popc(bal & ((1u << (c & 31)) - 1u));
+        if (on && rank < kMaxLetters) s_letter[rank] = (unsigned char)c;
+        if (c == 0) s_n = total;
+        if (blockIdx.x == 0 && c < 256) lmap[c] = (unsigned char)((on && rank < kMaxLetters) ? rank : kMaxLetters);
+        if (blockIdx.x == 0 && c == 0) *nletters = total;
+        __syncthreads();
+    }
+    const int nl = s_n;
+    if (nl > kMaxLetters) return;          // the table is not used: the character-compare instantiation runs
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const long long per_pair = (long long)(nl + 1) * prof_stride;
+    for (long long x = tid; x < per_pair * npairs; x += nth) {
+        const long long pair = x / per_pair, y = x % per_pair;
+        const int r = (int)(y / prof_stride);
+        const long long w = y % prof_stride;
+        const int row = (r == nl) ? kMaxLetters : r;
+        const unsigned char* ap = a + pair * m;
+        const long long base = 4 * (w - kProfPad) - 1;
+        int k[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long idx = base + e;
+            const bool hit = row < kMaxLetters && idx >= 0 && idx < m && ap[idx] == s_letter[row];
+            k[e] = hit ? s_match : s_mismatch;
+        }
+        prof[pair * prof_pair_stride + (long long)row * prof_stride + w] = make_int4(k[0], k[1], k[2], k[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // compute warp
 // ---------------------------------------------------------------------------------
-template <int KT, bool STORE>
+template <int KT, bool STORE, bool PROF>
 struct Strip {
     static constexpr int kRowInts = 4 * KT;
     int lane;
@@ -339,6 +415,26 @@ struct Strip {
     int   rmax[kR], rcol[kR];     // score-only: best clean 16*H of each of my rows and its first column
     int   kmax;                   // full fill: largest key of my cells in columns 1..m (strip maximum; the writers have no
                                   // ALU slots to spare for it)
+    // PROF: score profile rows of my rows (pointer to the block of this group's first step) and the scores of the
+    // next kProfDepth steps; `one` is an opaque 1, the multiplier of the IMADs that keep the additions off the ALU pipe
+    const int4* pg[kR];
+    static constexpr int kProfDepth = prof_depth(KT, STORE);
+    int4  pf[kR][kProfDepth];
+    int   one;
+
+    static __device__ __forceinline__ int4 ldg_prof(const int4* p)
+    {
+        int4 v;
+        asm("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        return v;
+    }
+    // x + y on the FMA pipe (IMAD with a register multiplier that ptxas cannot fold)
+    __device__ __forceinline__ int addf(const int x, const int y) const
+    {
+        int d;
+        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(y));
+        return d;
+    }
 
     __device__ __forceinline__ void scores(const unsigned aword)
     {
@@ -399,20 +495,54 @@ struct Strip {
             v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
         }
 
+        // this step's scores from the profile; the slot is refilled with the scores of step t + kProfDepth
+        int4 sc[kR];
+        if constexpr (PROF) {
+#pragma unroll
+            for (int q = 0; q < kR; ++q) {
+                sc[q] = pf[q][I & (kProfDepth - 1)];
+                pf[q][I & (kProfDepth - 1)] = ldg_prof(pg[q] + (I + kProfDepth));
+            }
+            if (MODE & 1) {
+                // head of a strip in column-strip mode (see head_fix): blocks j < 0 and column 0 cannot take the
+                // diagonal, and the boundary value enters as the left neighbour of block 0
+#pragma unroll
+                for (int q = 0; q < kR; ++q) {
+                    sc[q].x = (j <= 0) ? kSNeg : sc[q].x;
+                    sc[q].y = (j < 0) ? kSNeg : sc[q].y;
+                    sc[q].z = (j < 0) ? kSNeg : sc[q].z;
+                    sc[q].w = (j < 0) ? kSNeg : sc[q].w;
+                    hl[q] = (j == 0) ? lb[q] : hl[q];
+                }
+            }
+        }
+
         // K = max(left+gap|LEFT, up+gap|UP, diag+s|DIAG, 0|NONE)     (omp_smithW.c:339-381)
         int u0 = A0, u1 = A1, u2 = A2, u3 = A3, dg = dgp;
         dgp = A3;
         int n0, n1, n2, n3;
 #pragma unroll
         for (int q = 0; q < kR; ++q) {
-            const int p0 = __viaddmax_s32(dg, s[q][0], kTieNone);
-            const int p1 = __viaddmax_s32(u0, s[q][1], kTieNone);
-            const int p2 = __viaddmax_s32(u1, s[q][2], kTieNone);
-            const int p3 = __viaddmax_s32(u2, s[q][3], kTieNone);
-            const int t0 = __viaddmax_s32(u0, gu, p0);
-            const int t1 = __viaddmax_s32(u1, gu, p1);
-            const int t2 = __viaddmax_s32(u2, gu, p2);
-            const int t3 = __viaddmax_s32(u3, gu, p3);
+            int t0, t1, t2, t3;
+            if constexpr (PROF) {
+                // the two candidates that do not depend on this row are formed on the FMA pipe (IMAD) and folded
+                // with the NONE key by one three-input maximum: 3 ALU-pipe instructions per cell instead of 6.5
+                const int d0 = addf(dg, sc[q].x), d1 = addf(u0, sc[q].y), d2 = addf(u1, sc[q].z), d3 = addf(u2, sc[q].w);
+                const int v0 = addf(u0, gu), v1 = addf(u1, gu), v2 = addf(u2, gu), v3 = addf(u3, gu);
+                t0 = __vimax3_s32(d0, v0, kTieNone);
+                t1 = __vimax3_s32(d1, v1, kTieNone);
+                t2 = __vimax3_s32(d2, v2, kTieNone);
+                t3 = __vimax3_s32(d3, v3, kTieNone);
+            } else {
+                const int p0 = __viaddmax_s32(dg, s[q][0], kTieNone);
+                const int p1 = __viaddmax_s32(u0, s[q][1], kTieNone);
+                const int p2 = __viaddmax_s32(u1, s[q][2], kTieNone);
+                const int p3 = __viaddmax_s32(u2, s[q][3], kTieNone);
+                t0 = __viaddmax_s32(u0, gu, p0);
+                t1 = __viaddmax_s32(u1, gu, p1);
+                t2 = __viaddmax_s32(u2, gu, p2);
+                t3 = __viaddmax_s32(u3, gu, p3);
+            }
             dg = hl[q];                                  // diagonal of the next row's first cell
 #ifdef SWB_CLEAN_CHAIN
             // the left-to-right chain carries clean 16*H values only: floor16(max(x + gl, T)) =
@@ -495,8 +625,10 @@ struct Strip {
             st_cg_int4_if<16 * I>(gout, o, out_glob & started);
         }
         // ---------------- scores of the next step ----------------
-        if (MODE & 1) head_fix(next_word, j + 1);
-        else          scores(next_word);
+        if constexpr (!PROF) {
+            if (MODE & 1) head_fix(next_word, j + 1);
+            else          scores(next_word);
+        }
 
         // ---------------- the row above, for the next step ----------------
         // (v is valid by construction: compute_strip waited for the last block of this run of steps.  A tag
@@ -514,8 +646,8 @@ struct Strip {
 // the staged data and its flag relies on the in-order shared-memory pipeline of one warp
 // (data STS, __syncwarp, flag STS; flag LDS, data LDS): a MEMBAR here waits for the writer's
 // outstanding GLOBAL stores as well and cost ~2500 clk per round.
-template <int KT, bool STORE>
-__device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STORE>& S, const unsigned* aw,
+template <int KT, bool STORE, bool PROF>
+__device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STORE, PROF>& S, const unsigned* aw,
                                               const unsigned staged, const unsigned drained,
                                               const unsigned consumed_in, const unsigned consumed_out,
                                               const bool ring_consumer, const long long strip)
@@ -523,8 +655,17 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
     const int lane = S.lane;
     trace_stamp(p, strip, 0, lane);
     unsigned cur[kGroup + 1], nxt[kGroup];
+    if constexpr (PROF) {
 #pragma unroll
-    for (int i = 0; i < kGroup; ++i) cur[i] = __ldg(aw + i);
+        for (int i = 0; i < kGroup + 1; ++i) cur[i] = 0;
+#pragma unroll
+        for (int q = 0; q < kR; ++q)
+#pragma unroll
+            for (int i = 0; i < prof_depth(KT, STORE); ++i) S.pf[q][i] = Strip<KT, STORE, PROF>::ldg_prof(S.pg[q] + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kGroup; ++i) cur[i] = __ldg(aw + i);
+    }
 
     // first input block (block 0 -> ring index 32, epoch 0 -> tag 1); all lanes poll
     if (S.has_in) {
@@ -536,9 +677,12 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 #ifdef SWB_X_CLKTRACE
     const long long clk_gate = clock64();
 #endif
-    const bool forced = (STORE && p.left_in != nullptr) || opaque(*p.nul_flag) != 0;
-    if (forced) S.head_fix(cur[0], -lane);
-    else        S.scores(cur[0]);
+    // (with the score profile a NUL byte in b needs no care: positions outside a never match whatever the letter)
+    const bool forced = (STORE && p.left_in != nullptr) || (!PROF && opaque(*p.nul_flag) != 0);
+    if constexpr (!PROF) {
+        if (forced) S.head_fix(cur[0], -lane);
+        else        S.scores(cur[0]);
+    }
 
     const int gtail = (p.jmax - 8) >> 3;          // groups g <= gtail: t+1 <= jmax for all their steps
     int known_drained = 0, known_consumed = 0;
@@ -582,9 +726,11 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 #endif
         sts_volatile_int_if(consumed_in, t0, S.has_in & (lane == 0 ? 1 : 0));
         // ---- sequence words of the next group
+        if constexpr (!PROF) {
 #pragma unroll
-        for (int i = 0; i < kGroup; ++i) nxt[i] = __ldg(aw + t0 + kGroup + i);
-        cur[kGroup] = nxt[0];
+            for (int i = 0; i < kGroup; ++i) nxt[i] = __ldg(aw + t0 + kGroup + i);
+            cur[kGroup] = nxt[0];
+        }
 
         // consumer side: block t -> ring index (t+32)&63, epoch ((t+32)>>6)&1
         const unsigned in_g  = S.ring_in + 16u * (unsigned)((t0 + 32) & (kRing - 1));
@@ -640,8 +786,13 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         const long long gc2 = clock64();
 #endif
         S.gout += kGroup;
+        if constexpr (PROF) {
 #pragma unroll
-        for (int i = 0; i < kGroup; ++i) cur[i] = nxt[i];
+            for (int q = 0; q < kR; ++q) S.pg[q] += kGroup;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kGroup; ++i) cur[i] = nxt[i];
+        }
         // ---- publish the staged group to the writers
         __syncwarp();
         if (STORE) sts_volatile_int_if(staged, g + 1, lane == 0 ? 1 : 0);
@@ -936,10 +1087,12 @@ __host__ __device__ constexpr size_t fill_smem_bytes(int wpc, int KT, bool store
 // band boundary.  dynamic smem = fill_smem_bytes(wpc, KT, STORE).
 // STORE = false is the score-only variant: no staging, no writers, per-row best cells instead.
 // ---------------------------------------------------------------------------------
-template <int KT, bool STORE>
+template <int KT, bool STORE, bool PROF>
 __global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true), (KT == 64 && STORE) ? 1 : 2)
 fill_kernel(const FillParams p_in)
 {
+    // both instantiations are launched; the alphabet of b (counted on the device by profile_kernel) decides which runs
+    if ((*p_in.nletters <= kMaxLetters) != PROF) return;
     extern __shared__ __align__(1024) int4 smem4[];
     __shared__ int s_band;
     __shared__ int s_staged[kMaxWpc], s_drained[kMaxWpc * kWriters], s_consumed[kMaxWpc + 1];
@@ -981,6 +1134,7 @@ fill_kernel(const FillParams p_in)
     const int band = s_band % p_in.nbands;
     FillParams p = p_in;
     p.a4 += pair * p.a4_stride;
+    p.prof += pair * p.prof_pair_stride;
     p.b += pair * p.n;
     p.H += pair * p.pair_stride; p.P += pair * p.pair_stride;
     p.boundary += pair * (long long)(p.nbands - 1) * p.bstride;
@@ -993,7 +1147,7 @@ fill_kernel(const FillParams p_in)
         // ------------------------------------------------ compute
         const long long r0 = band_r0 + (long long)kStripRows * w;
         if (r0 > p.n) return;
-        Strip<KT, STORE> S;
+        Strip<KT, STORE, PROF> S;
         S.lane = lane;
 #pragma unroll
         for (int q = 0; q < kR; ++q) {
@@ -1001,7 +1155,12 @@ fill_kernel(const FillParams p_in)
             S.b4[q] = (row <= p.n) ? (unsigned)p.b[row - 1] * 0x01010101u : 0u;
             S.inv[q] = (row <= p.n) ? 0u : 0x01010101u;
             S.hl[q] = 0; S.rmax[q] = 0; S.rcol[q] = 0; S.kmax = 0;
+            if constexpr (PROF) {
+                const int li = (row <= p.n) ? (int)p.lmap[p.b[row - 1]] : kMaxLetters;
+                S.pg[q] = p.prof + (long long)li * p.prof_stride + kProfPad - lane;      // block -lane of step 0
+            }
         }
+        S.one = opaque(1);
         // keep the scoring constants in registers: a shuffle result is opaque to ptxas, which
         // otherwise re-reads them from the constant bank at the head of every step, on the
         // dependency chain
@@ -1050,7 +1209,7 @@ fill_kernel(const FillParams p_in)
         S.gout = p.boundary + (size_t)(next_row && (w + 1 == wpc) ? band : 0) * p.bstride + kBoundaryPad - lane;
         const unsigned* aw = p.a4 + kAPad - lane;                // aw[t] = characters of block t - lane
         const long long strip = (r0 - 1) / kStripRows;
-        compute_strip<KT, STORE>(p, S, aw, (unsigned)__cvta_generic_to_shared(s_staged + w),
+        compute_strip<KT, STORE, PROF>(p, S, aw, (unsigned)__cvta_generic_to_shared(s_staged + w),
                       (unsigned)__cvta_generic_to_shared(s_drained + w * kWriters),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, strip + pair * p.nstrips);
