@@ -12,8 +12,9 @@
  * Every entry point below names the reference interface it replaces.  All of
  * them return 0 on success and a negative swb_status otherwise (the reference
  * prints and exit(0)s on CUDA errors, simple-cuda/sw-default-discrete.cu:101-108;
- * we never exit).  No global state; calls on different streams/devices are
- * independent.  There is NO CPU fallback: without a CUDA device every compute
+ * we never exit).  Calls on different streams/devices are independent; the only
+ * process-wide state is one private CUDA memory pool per device for the per-call
+ * workspace (it keeps at most 2 GB of freed blocks; the default pool is not touched).  There is NO CPU fallback: without a CUDA device every compute
  * entry point returns SWB_ERR_CUDA.
  *
  * Data contract (identical to the reference, omp_smithW.c:109-118,336):
@@ -180,6 +181,12 @@ int swb_shard_pairs(int64_t npairs, int nshards, int shard, int64_t* first, int6
  *   epoch       nonzero, different from the previous call's on the same buffers
  * The fill kernel of strip g+1 waits on the flags piece by piece, so all strips run concurrently,
  * each a few row-blocks behind its left neighbour; there is no collective in the data path.
+ * Ordering rules for the caller: (1) strips that share a device must be enqueued left to right on ONE stream;
+ * (2) the boundary buffers of a call may be reused only after the right neighbour has finished the call that
+ * read them (swb_multi_* synchronises every stream per call; strips.StripPipeline separates calls by the maxPos
+ * all-gather or a barrier) -- alternate two buffer sets by call parity to let the left GPU start early;
+ * (3) a strip whose left neighbour never publishes its flags traps after ~10 s of waiting (the launch fails
+ * with a CUDA error) instead of hanging.
  * d_maxPos / d_maxScore: the LOCAL maximum over local columns 1..m_local (index i*pitch + j_local,
  * reference tie-break).  In P, local column 0 of a strip with a left neighbour holds 5 (not a
  * reference code): the backtrack hand-off marker. */

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace {
 
@@ -78,26 +79,41 @@ struct Workspace {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// The workspace comes from the stream-ordered pool on every call: keep freed blocks in the pool
-// (the default release threshold of 0 hands them back to the driver at every synchronisation,
-// which costs milliseconds per call for the ~100 MB of band-boundary rows).
-void keep_pool_warm(int device)
+// The workspace comes from a stream-ordered pool on every call.  The library owns one PRIVATE pool per device
+// (the process's default pool and its release threshold are left alone): freed blocks stay in it up to
+// kPoolKeepBytes, because handing ~100 MB of band-boundary rows back to the driver at every synchronisation
+// (release threshold 0) costs milliseconds per call.  This table is the library's only process-wide state.
+constexpr unsigned long long kPoolKeepBytes = 2ull << 30;
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[64] = {};
+
+cudaMemPool_t workspace_pool(int device)
 {
-    static bool done[64] = {};
-    if (device < 0 || device >= 64 || done[device]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+            unsigned long long keep = kPoolKeepBytes;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            g_pools[device] = pool;
+        }
+        cudaGetLastError();
     }
-    cudaGetLastError();
-    done[device] = true;
+    return g_pools[device];
 }
 
 int pick_wpc(int64_t n, int64_t npairs, int kt, bool store, const swb_tuning* tuning)
 {
     int wpc = (npairs > 1) ? 1 : 2;         // measured: 65536 x 256x256 pairs 295 vs 247 GCUPS with 1 strip per CTA
+#ifdef SWB_DEV_KNOBS
     if (const char* e = std::getenv("SWB_WPC")) wpc = std::atoi(e);
+#endif
     if (tuning && tuning->warps_per_band > 0) wpc = tuning->warps_per_band;
     wpc = std::max(1, std::min(wpc, swb::kMaxWpc));
     while (wpc > 1 && swb::fill_smem_bytes(wpc, kt, store) + 2048 > 227 * 1024) --wpc;     // 227 KB of shared memory per CTA on sm_100
@@ -147,17 +163,19 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
     if (store && pitch >= (1LL << 23)) return SWB_ERR_RANGE;      // the writers address a strip with 32-bit byte offsets (64 rows * pitch * 4)
     if (store && ((reinterpret_cast<uintptr_t>(dH) & 15) || (reinterpret_cast<uintptr_t>(dP) & 15))) return SWB_ERR_ALIGN;
     const swb_scoring sc = scoring ? *scoring : kDefaultScoring;
-    if (int rc = check_scoring(sc, m, n)) return rc;
+    // (column-strip mode: m is the LOCAL width; the scores are bounded by the whole pair's min(m_total, n) <= n)
+    if (int rc = check_scoring(sc, link ? n : m, n)) return rc;
     if (!store) pitch = m + 1;
 
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    keep_pool_warm(device);
 
     // single large pairs: deep staging ring, one CTA per SM; batches of small pairs: shallow ring, more CTAs per SM
     int kt = (npairs > 1) ? 32 : 64;
+#ifdef SWB_DEV_KNOBS
     if (const char* e = std::getenv("SWB_KT")) kt = (std::atoi(e) == 32) ? 32 : 64;     // developer knob
+#endif
     const int wpc = pick_wpc(n, npairs, kt, store, tuning);
     const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
     const int nbands = (int)((strips + wpc - 1) / wpc);
@@ -185,7 +203,8 @@ int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs
     const size_t boundary_bytes = (size_t)npairs * (size_t)std::max(nbands - 1, 0) * (size_t)ws.bstride * sizeof(int4);
     const size_t o_bnd = carve(boundary_bytes);
     const size_t o_rb = carve(store ? 0 : (size_t)npairs * (size_t)(n + 1) * sizeof(unsigned long long));
-    SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws.base), off, st));
+    if (cudaMemPool_t pool = workspace_pool(device)) SWB_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&ws.base), off, pool, st));
+    else                                             SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws.base), off, st));
     ws.a4 = reinterpret_cast<unsigned*>(ws.base + o_a4);
     ws.a_dev = ws.base + o_a; ws.b_dev = ws.base + o_b;
     ws.ticket = reinterpret_cast<int*>(ws.base + o_small);
@@ -508,6 +527,7 @@ int swb_backtrack_from_async(int32_t* dP, int64_t pitch, int64_t startPos, int64
                              int device, void* stream)
 {
     if (!dP || pitch <= 1 || startPos < 0) return SWB_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(dP) & 15) return SWB_ERR_ALIGN;      // band rows are fetched with 16-byte bulk copies
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -523,6 +543,7 @@ int swb_backtrack_async(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_
                         int64_t* d_pathLen, int device, void* stream)
 {
     if (!dP || pitch <= 1 || (!d_maxPos && maxPos < 0)) return SWB_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(dP) & 15) return SWB_ERR_ALIGN;      // band rows are fetched with 16-byte bulk copies
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -117,6 +117,7 @@ constexpr int kBoundaryPad = 32;       // spare blocks in front of a band-bounda
 constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: compute warps on schedulers 0..wpc-1,
                                        // writers + loader on the others
 constexpr int kDrainRounds = 2;        // writer rounds after the last compute group
+constexpr unsigned kGateSpinLimit = 40u << 20;   // polls (>= 200 ns each: ~10 s or more) a strip waits for its left GPU before it traps
 #ifndef SWB_KMAX_IN_COMPUTE
 #define SWB_KMAX_IN_COMPUTE 1          // who keeps the strip maximum: the compute warp (1) or its writers (0); the single-pair
                                        // full fill (KT == 64) always leaves it to the writers: 1 % faster there, while the
@@ -1182,9 +1183,15 @@ fill_kernel(const FillParams p_in)
                     if (r0 + kWRows * k > p.n) break;
                     const int* f = p.left_flags + (r0 - 1) / kWRows + k;
                     int v;
+                    unsigned spins = 0;
                     do {
                         asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                        if (v != p.epoch) __nanosleep(200);
+                        if (v != p.epoch) {
+                            __nanosleep(200);
+                            // bounded: if the left neighbour never runs (it failed, or the caller enqueued the strips in
+                            // the wrong order on one device) the launch ends with an error instead of hanging the GPU
+                            if (++spins > kGateSpinLimit) __trap();
+                        }
                     } while (v != p.epoch);
                 }
 #pragma unroll

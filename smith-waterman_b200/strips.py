@@ -306,12 +306,24 @@ class StripPipeline:
         if self.rank + 1 < self.world:
             self.strip.connect_right_ipc(bytes(allh[self.rank + 1].cpu().numpy().tobytes()))
         self.dist.barrier()
+        self._unjoined_fills = 0
 
     def fill_async(self, stream=None, timer=None):
+        # Back-pressure (the boundary buffers are double-buffered by call parity): a rank may start call k+1 only after
+        # every rank has finished call k-1, or the left GPU would overwrite values its right neighbour is still
+        # reading.  maxpos() is such a point (local_max() synchronises this rank's fill, the all-gather joins the
+        # ranks); two fills without it in between are separated by an explicit barrier here.
+        if self._unjoined_fills >= 1:
+            self.torch.cuda.synchronize(self.device)
+            self.dist.barrier()
+            self._unjoined_fills = 0
         self.strip.fill_async(stream=stream, timer=timer)
+        self._unjoined_fills += 1
 
     def maxpos(self) -> int:
-        return allgather_maxpos(self.strip.local_max(), self.m, self.dist, self.tdev)
+        mp = allgather_maxpos(self.strip.local_max(), self.m, self.dist, self.tdev)
+        self._unjoined_fills = 0
+        return mp
 
     def backtrack(self, maxPos: int) -> int:
         return distributed_backtrack(self.parts, maxPos, self.m, self.rank, self.strip.walk, self.dist, self.tdev)

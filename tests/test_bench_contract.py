@@ -9,7 +9,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 def test_reference_arm_prints_one_contract_line():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-sample", "1024"], capture_output=True, text=True, timeout=300)
+                          "--cpu-sample", "1024", "--ref-full", "0"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -25,6 +25,6 @@ def test_reference_arm_prints_one_contract_line():
 def test_other_ranks_of_the_reference_arm_exit_quietly():
     import os
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
-    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-full", "0"],
                          capture_output=True, text=True, timeout=60, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""

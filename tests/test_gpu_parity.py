@@ -76,10 +76,19 @@ def test_hashed_dumps_of_the_reference(swb, oracle, golden_dir):
         assert f"{oracle.fnv(P):016x}" == c["Pbt_fnv"], c
 
 
-@pytest.mark.parametrize("wpc", [1, 2, 4, 8, 16])
-def test_random_shapes_all_phases(swb, oracle, wpc):
+# alphabets: 4 letters -> the score-profile instantiation of the fill kernel (at most 8 distinct bytes in b);
+# 12 letters -> the character-compare instantiation; 8 letters incl. NUL -> the profile's padding must not match NUL
+ALPHABETS = {"dna": ACGT, "wide": np.frombuffer(b"ACDEFGHIKLMN", dtype=np.uint8),
+             "nul8": np.array([0, 65, 67, 71, 84, 78, 1, 255], dtype=np.uint8),
+             "nul12": np.arange(12, dtype=np.uint8)}
+
+
+@pytest.mark.parametrize("wpc,alpha", [(1, "dna"), (2, "dna"), (1, "wide"), (2, "wide"), (2, "nul8"), (2, "nul12"), (16, "dna")])
+def test_random_shapes_all_phases(swb, oracle, wpc, alpha):
     # every pitch phase (m+1 mod 4), partial last strips, single rows/columns, sizes
-    # straddling the 32-row strip, the 8-step group and the fast/edge switch
+    # straddling the 64-row strip, the 8-step group and the fast/edge switch
+    # (warps_per_band > 2 is clamped to 2: the (16, "dna") case checks the clamp, not a new configuration)
+    ACGT = ALPHABETS[alpha]
     rng = np.random.default_rng(100 + wpc)
     shapes = [(1, 1), (1, 77), (77, 1), (2, 3), (31, 32), (32, 33), (33, 31), (63, 65), (127, 129), (128, 128),
               (255, 31), (256, 256), (257, 259), (258, 64), (259, 97), (511, 300), (700, 513), (1025, 130),
@@ -163,6 +172,12 @@ def test_error_behaviour(swb):
         swb.fill(b"ACGT", 4, b"ACG", 3, dH.data_ptr() + 4, dH, pitch=5)   # misaligned
     with pytest.raises(swb.SwbError):
         swb.fill(b"ACGT", 0, b"ACG", 3, dH, dH)
+    # backtrack stages band rows with 16-byte bulk copies: a misaligned P is an error code, not a device fault
+    with pytest.raises(swb.SwbError):
+        swb.backtrack(dH.data_ptr() + 4, 5, 7)
+    with pytest.raises(swb.SwbError):
+        swb.backtrack_async(dH.data_ptr() + 8, 5, 7)
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize("cols,rows,seed", [(8192, 8192, 42), (20000, 3000, 5), (3000, 20000, 6)])
