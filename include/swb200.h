@@ -231,6 +231,19 @@ int  swb_fill_multi(const char* a, int64_t m, const char* b, int64_t n, const sw
                     const int* devices, int ndev, int32_t* H, int32_t* P,
                     int64_t* maxPos, int64_t* path_len, int do_backtrack);
 
+/* ---- alignment emission: the step right after backtrack(P, maxPos) (omp_smithW.c:405-420), which
+ * only negates the path.  swb_traceback_async is swb_backtrack_from_async that also writes the moves of the path
+ * to d_moves (DEVICE, one byte per path cell, capacity >= n + m; may be NULL), in walk order = from the start cell
+ * backwards: 1 UP, 2 LEFT, 3 DIAGONAL (the P codes, omp_smithW.c:33-36).  d_startPos (DEVICE int64, e.g. the d_maxPos
+ * of swb_fill_async) takes precedence over startPos.  The host helpers turn moves into a CIGAR string (sequence
+ * order; a = columns is the reference, b = rows the query: DIAGONAL -> M, UP -> I, LEFT -> D; returns the length the
+ * string needs, writes at most cap-1 characters + NUL) and into the two gapped strings (out_a, out_b: n+1 bytes). */
+int swb_traceback_async(int32_t* dP, int64_t pitch, int64_t startPos, const int64_t* d_startPos, int64_t* d_pathLen,
+                        int64_t* d_endPos, unsigned char* d_moves, int device, void* stream);
+int64_t swb_cigar_from_moves(const unsigned char* moves, int64_t n, char* cigar, size_t cap);
+int swb_alignment_from_moves(const unsigned char* moves, int64_t n, const char* a, const char* b, int64_t startPos,
+                             int64_t pitch, char* out_a, char* out_b);
+
 /* Boundary buffers that another process maps (cudaMalloc + CUDA IPC): allocation (zero-filled),
  * 64-byte IPC handle, mapping a peer's handle on `device`, and peer access between two devices of
  * one process. */

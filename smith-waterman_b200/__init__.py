@@ -20,7 +20,7 @@ from pathlib import Path
 __all__ = ["lib", "SwbError", "Scoring", "DEFAULT_SCORING", "generate", "fill", "fill_async", "fill_batch_async", "score_only_async", "backtrack", "backtrack_async",
            "smithWaterman", "align_host", "AlignContext", "score_only", "KernelTimer", "host_alloc", "host_free",
            "device_count", "LIB_PATH", "NONE", "UP", "LEFT", "DIAGONAL", "PATH",
-           "fill_pairs_async", "shard_pairs", "MultiGpuPair", "read_sequences", "read_sequence", "load_manifest"]
+           "fill_pairs_async", "shard_pairs", "MultiGpuPair", "traceback_async", "cigar_from_moves", "alignment_from_moves", "read_sequences", "read_sequence", "load_manifest"]
 
 # omp_smithW.c:32-36
 PATH, NONE, UP, LEFT, DIAGONAL = -1, 0, 1, 2, 3
@@ -108,6 +108,10 @@ def _load() -> C.CDLL:
     L.swb_manifest_pairs.argtypes = [vp]; L.swb_manifest_pairs.restype = i64
     L.swb_manifest_pair.argtypes = [vp, i64, C.POINTER(vp), pi64, C.POINTER(vp), pi64]
     L.swb_manifest_free.argtypes = [vp]; L.swb_manifest_free.restype = None
+    L.swb_traceback_async.argtypes = [vp, i64, i64, vp, vp, vp, vp, C.c_int, vp]
+    L.swb_cigar_from_moves.argtypes = [vp, i64, C.c_char_p, C.c_size_t]; L.swb_cigar_from_moves.restype = i64
+    L.swb_alignment_from_moves.argtypes = [vp, i64, vp, vp, i64, i64, C.c_char_p, C.c_char_p]
+    L.swb_traceback_async.restype = C.c_int; L.swb_alignment_from_moves.restype = C.c_int
     for name in ("swb_fill_pairs_async", "swb_shard_pairs", "swb_multi_create", "swb_multi_fill", "swb_multi_backtrack",
                  "swb_multi_align", "swb_multi_strips", "swb_multi_strip", "swb_multi_gather_host", "swb_fill_multi",
                  "swb_seq_count", "swb_seq_read", "swb_manifest_load", "swb_manifest_pair"):
@@ -423,3 +427,30 @@ def load_manifest(path):
         return out
     finally:
         lib.swb_manifest_free(h)
+
+
+# ---------------------------------------------------------------------------------------------
+# alignment emission
+# ---------------------------------------------------------------------------------------------
+def traceback_async(dP, pitch: int, startPos: int = 0, d_startPos=None, d_pathLen=None, d_endPos=None, d_moves=None,
+                    device: int = 0, stream=None) -> None:
+    """backtrack that also writes the path's moves (device uint8 buffer, walk order; 1 UP, 2 LEFT, 3 DIAGONAL)"""
+    _check(lib.swb_traceback_async(_ptr(dP), pitch, startPos, _ptr(d_startPos), _ptr(d_pathLen), _ptr(d_endPos),
+                                   _ptr(d_moves), device, _stream_ptr(stream)))
+
+
+def cigar_from_moves(moves: bytes) -> str:
+    """moves in walk order -> CIGAR in sequence order (a = reference, b = query: M / I (UP) / D (LEFT))"""
+    need = lib.swb_cigar_from_moves(_ptr(moves), len(moves), None, 0)
+    if need < 0:
+        _check(int(need))
+    buf = C.create_string_buffer(need + 1)
+    lib.swb_cigar_from_moves(_ptr(moves), len(moves), buf, need + 1)
+    return buf.value.decode()
+
+
+def alignment_from_moves(moves: bytes, a: bytes, b: bytes, startPos: int, pitch: int):
+    """-> (gapped a, gapped b) as bytes"""
+    oa, ob = C.create_string_buffer(len(moves) + 1), C.create_string_buffer(len(moves) + 1)
+    _check(lib.swb_alignment_from_moves(_ptr(moves), len(moves), _ptr(a), _ptr(b), startPos, pitch, oa, ob))
+    return oa.value, ob.value

@@ -2,12 +2,17 @@
 // Host code is plain C++/CUDA runtime; no torch types, no CPU fallback.
 #include "../../include/swb200.h"
 #include "swb_kernels.cuh"
+#include "swb_backtrack.cuh"
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+
+#ifndef SWB_BT2
+#define SWB_BT2 0                      // 1: the jump-table backtrack kernel (swb_backtrack.cuh); 0: the single-walker kernel
+#endif
 
 namespace {
 
@@ -523,35 +528,94 @@ int swb_fill(const char* a, int64_t m, const char* b, int64_t n,
     return rc;
 }
 
-int swb_backtrack_from_async(int32_t* dP, int64_t pitch, int64_t startPos, int64_t* d_pathLen, int64_t* d_endPos,
-                             int device, void* stream)
-{
-    if (!dP || pitch <= 1 || startPos < 0) return SWB_ERR_ARG;
-    if (reinterpret_cast<uintptr_t>(dP) & 15) return SWB_ERR_ALIGN;      // band rows are fetched with 16-byte bulk copies
-    DeviceGuard guard(device);
-    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int bt_smem = (2 * (swb::kBtPad + swb::kBtBandInts) + 2 * swb::kBtList) * (int)sizeof(int);
-    SWB_CUDA(cudaFuncSetAttribute(swb::backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt_smem));
-    swb::backtrack_kernel<<<1, swb::kBtThreads, bt_smem, st>>>(dP, pitch, startPos, nullptr, reinterpret_cast<long long*>(d_pathLen),
-                                                               reinterpret_cast<long long*>(d_endPos));
-    SWB_CUDA(cudaGetLastError());
-    return SWB_OK;
-}
-
-int swb_backtrack_async(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_t* d_maxPos,
-                        int64_t* d_pathLen, int device, void* stream)
+}  // extern "C"
+namespace {
+// the one backtrack launch: start cell from d_maxPos (device) or maxPos; optional path length, end cell and moves
+int launch_backtrack(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_t* d_maxPos, int64_t* d_pathLen,
+                     int64_t* d_endPos, unsigned char* d_moves, int device, void* stream)
 {
     if (!dP || pitch <= 1 || (!d_maxPos && maxPos < 0)) return SWB_ERR_ARG;
     if (reinterpret_cast<uintptr_t>(dP) & 15) return SWB_ERR_ALIGN;      // band rows are fetched with 16-byte bulk copies
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+#if SWB_BT2
+    SWB_CUDA(cudaFuncSetAttribute(swb::bt2::backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, swb::bt2::kSmemBytes));
+    swb::bt2::backtrack_kernel<<<1, swb::bt2::kThreads, swb::bt2::kSmemBytes, st>>>(
+        dP, pitch, maxPos, reinterpret_cast<const long long*>(d_maxPos), reinterpret_cast<long long*>(d_pathLen),
+        reinterpret_cast<long long*>(d_endPos), d_moves);
+#else
+    if (d_moves) return SWB_ERR_ARG;                                      // (the single-walker kernel does not emit moves)
     const int bt_smem = (2 * (swb::kBtPad + swb::kBtBandInts) + 2 * swb::kBtList) * (int)sizeof(int);
     SWB_CUDA(cudaFuncSetAttribute(swb::backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt_smem));
     swb::backtrack_kernel<<<1, swb::kBtThreads, bt_smem, st>>>(dP, pitch, maxPos, reinterpret_cast<const long long*>(d_maxPos),
-                                            reinterpret_cast<long long*>(d_pathLen), nullptr);
+                                                               reinterpret_cast<long long*>(d_pathLen),
+                                                               reinterpret_cast<long long*>(d_endPos));
+#endif
     SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+}  // namespace
+extern "C" {
+
+int swb_backtrack_from_async(int32_t* dP, int64_t pitch, int64_t startPos, int64_t* d_pathLen, int64_t* d_endPos,
+                             int device, void* stream)
+{
+    return launch_backtrack(dP, pitch, startPos, nullptr, d_pathLen, d_endPos, nullptr, device, stream);
+}
+
+int swb_backtrack_async(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_t* d_maxPos,
+                        int64_t* d_pathLen, int device, void* stream)
+{
+    return launch_backtrack(dP, pitch, maxPos, d_maxPos, d_pathLen, nullptr, nullptr, device, stream);
+}
+
+int swb_traceback_async(int32_t* dP, int64_t pitch, int64_t startPos, const int64_t* d_startPos, int64_t* d_pathLen,
+                        int64_t* d_endPos, unsigned char* d_moves, int device, void* stream)
+{
+    return launch_backtrack(dP, pitch, startPos, d_startPos, d_pathLen, d_endPos, d_moves, device, stream);
+}
+
+// moves in walk order (from the start cell backwards) -> CIGAR in sequence order.  a (columns) is the reference,
+// b (rows) the query: DIAGONAL consumes both (M), UP consumes a row = query only (I), LEFT a column = reference only (D).
+int64_t swb_cigar_from_moves(const unsigned char* moves, int64_t n, char* cigar, size_t cap)
+{
+    if (!moves || n < 0 || (!cigar && cap)) return SWB_ERR_ARG;
+    size_t used = 0;
+    int64_t k = n - 1;
+    while (k >= 0) {
+        const unsigned char mv = moves[k];
+        int64_t run = 0;
+        while (k >= 0 && moves[k] == mv) { ++run; --k; }
+        const char op = mv == 3 ? 'M' : mv == 1 ? 'I' : mv == 2 ? 'D' : '?';
+        char buf[32];
+        const int len = std::snprintf(buf, sizeof buf, "%lld%c", (long long)run, op);
+        if (cigar && used + (size_t)len < cap) std::memcpy(cigar + used, buf, (size_t)len);
+        used += (size_t)len;
+    }
+    if (cigar && cap) cigar[used < cap ? used : cap - 1] = 0;
+    return (int64_t)used;                                                 // length needed (without the NUL)
+}
+
+// the two gapped strings of the alignment ('-' = gap), sequence order; out_a / out_b hold n + 1 bytes.
+// startPos = the cell the walk started from (maxPos), pitch = ints per row of the matrix it indexes.
+int swb_alignment_from_moves(const unsigned char* moves, int64_t n, const char* a, const char* b, int64_t startPos,
+                             int64_t pitch, char* out_a, char* out_b)
+{
+    if (!moves || n < 0 || !a || !b || !out_a || !out_b || pitch <= 1) return SWB_ERR_ARG;
+    int64_t i = startPos / pitch, j = startPos % pitch;
+    for (int64_t k = 0; k < n; ++k) {
+        const int64_t o = n - 1 - k;
+        if (i < 1 && moves[k] != 2) return SWB_ERR_ARG;
+        if (j < 1 && moves[k] != 1) return SWB_ERR_ARG;
+        switch (moves[k]) {                                               // cell (i, j) pairs b[i-1] with a[j-1] (omp_smithW.c:395)
+        case 3: out_a[o] = a[j - 1]; out_b[o] = b[i - 1]; --i; --j; break;
+        case 1: out_a[o] = '-';      out_b[o] = b[i - 1]; --i; break;
+        case 2: out_a[o] = a[j - 1]; out_b[o] = '-';      --j; break;
+        default: return SWB_ERR_ARG;
+        }
+    }
+    out_a[n] = 0; out_b[n] = 0;
     return SWB_OK;
 }
 

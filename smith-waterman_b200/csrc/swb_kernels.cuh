@@ -76,6 +76,14 @@
 #define SWB_ST(p, v) __stwt(p, v)
 #endif
 
+#ifndef SWB_PROF_SMEM
+#define SWB_PROF_SMEM 1                // 1: the score profile is staged in a shared-memory ring by a feeder warp (one conflict-free
+                                       //    LDS.128 per row and step); 0: every lane loads its rows from global memory / L1
+#endif
+#ifndef SWB_PROF_PREFETCH
+#define SWB_PROF_PREFETCH 40           // SWB_PROF_SMEM == 0: blocks ahead of the current step that are prefetched into L1 (0 = off)
+#endif
+
 namespace swb {
 
 #ifndef SWB_ROWS_PER_LANE
@@ -112,7 +120,14 @@ constexpr int kProfRows   = kMaxLetters + 1;
 constexpr int kProfPad    = 32;        // leading pad blocks of a profile row (blocks -31..-1 of a strip's first steps)
 // prefetch distance in steps (power of two, <= kGroup): 4 in the single-pair full fill (one CTA per SM, registers to
 // spare), 2 in the batch and score-only instantiations (two CTAs per SM: 80 registers)
-__host__ __device__ constexpr int prof_depth(int KT, bool STORE) { return (KT == 64 && STORE) ? 4 : 2; }
+__host__ __device__ constexpr int prof_depth(int KT, bool STORE) { return SWB_PROF_SMEM ? 2 : ((KT == 64 && STORE) ? 4 : 2); }
+// shared-memory ring of the profile (SWB_PROF_SMEM): block j of letter row r sits in slot j & (kPRing - 1) of row r; the
+// first kPMirror slots are mirrored behind the ring so that the kGroup + depth loads of one group never wrap (their
+// offsets from the group's first slot are immediates).  The window a band needs is [lagging strip's block - 31,
+// leading strip's block + 8 + depth]; the hand-off credits keep the strips of a band within 88 steps of each other.
+constexpr int kPRing   = 256;
+constexpr int kPMirror = 16;
+constexpr int kPRowInt4 = kPRing + kPMirror;
 constexpr int kBoundaryPad = 32;       // spare blocks in front of a band-boundary row (blocks -31..-1 of a strip's first steps)
 constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: compute warps on schedulers 0..wpc-1,
                                        // writers + loader on the others
@@ -422,6 +437,8 @@ struct Strip {
     static constexpr int kProfDepth = prof_depth(KT, STORE);
     int4  pf[kR][kProfDepth];
     int   one;
+    unsigned rb[kR];              // SWB_PROF_SMEM: shared address of my rows' rows of the profile ring ...
+    unsigned rg[kR];              //                ... + the slot of this group's first step (block t0 - lane)
 
     static __device__ __forceinline__ int4 ldg_prof(const int4* p)
     {
@@ -502,7 +519,16 @@ struct Strip {
 #pragma unroll
             for (int q = 0; q < kR; ++q) {
                 sc[q] = pf[q][I & (kProfDepth - 1)];
+#if SWB_PROF_SMEM
+                pf[q][I & (kProfDepth - 1)] = lds_volatile_int4<16 * (I + kProfDepth)>(rg[q]);
+#else
                 pf[q][I & (kProfDepth - 1)] = ldg_prof(pg[q] + (I + kProfDepth));
+#endif
+#if !SWB_PROF_SMEM && SWB_PROF_PREFETCH > 0
+                // the leading lane of every letter touches a new 32-byte sector of its profile row every other step:
+                // bring it into L1 well ahead of the load (an L2 hit is ~4 steps away)
+                if ((I & 1) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(pg[q] + (I + SWB_PROF_PREFETCH)));
+#endif
             }
             if (MODE & 1) {
                 // head of a strip in column-strip mode (see head_fix): blocks j < 0 and column 0 cannot take the
@@ -651,18 +677,31 @@ template <int KT, bool STORE, bool PROF>
 __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STORE, PROF>& S, const unsigned* aw,
                                               const unsigned staged, const unsigned drained,
                                               const unsigned consumed_in, const unsigned consumed_out,
-                                              const bool ring_consumer, const long long strip)
+                                              const bool ring_consumer, const long long strip,
+                                              const unsigned progress, const unsigned fed)
 {
     const int lane = S.lane;
     trace_stamp(p, strip, 0, lane);
     unsigned cur[kGroup + 1], nxt[kGroup];
+    int known_fed = -(1 << 30);
     if constexpr (PROF) {
 #pragma unroll
         for (int i = 0; i < kGroup + 1; ++i) cur[i] = 0;
+#if SWB_PROF_SMEM
+        // the feeder warp publishes the number of profile blocks it has staged (blocks < fed are in the ring)
+        do { known_fed = lds_volatile_int(fed); } while (known_fed < kGroup + prof_depth(KT, STORE));
+#pragma unroll
+        for (int q = 0; q < kR; ++q) {
+            S.rg[q] = S.rb[q] + 16u * (unsigned)((0 - lane) & (kPRing - 1));
+#pragma unroll
+            for (int i = 0; i < prof_depth(KT, STORE); ++i) S.pf[q][i] = lds_volatile_int4<0>(S.rg[q] + 16u * (unsigned)i);
+        }
+#else
 #pragma unroll
         for (int q = 0; q < kR; ++q)
 #pragma unroll
             for (int i = 0; i < prof_depth(KT, STORE); ++i) S.pf[q][i] = Strip<KT, STORE, PROF>::ldg_prof(S.pg[q] + i);
+#endif
     } else {
 #pragma unroll
         for (int i = 0; i < kGroup; ++i) cur[i] = __ldg(aw + i);
@@ -726,6 +765,16 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         if (g >= SWB_X_GT_LO && g < SWB_X_GT_HI) { const long long gd2 = clock64(); dbg_drain += gd1 - gd0; dbg_cons += gd2 - gd1; }
 #endif
         sts_volatile_int_if(consumed_in, t0, S.has_in & (lane == 0 ? 1 : 0));
+#if SWB_PROF_SMEM
+        if constexpr (PROF) {
+            // profile ring: this group's loads reach block t0 + kGroup - 1 + depth (lane 0); tell the feeder where I am
+            const int need = t0 + kGroup + prof_depth(KT, STORE);
+            if (need > known_fed) { do { known_fed = lds_volatile_int(fed); } while (known_fed < need); }
+            sts_volatile_int_if(progress, t0, lane == 0 ? 1 : 0);
+#pragma unroll
+            for (int q = 0; q < kR; ++q) S.rg[q] = S.rb[q] + 16u * (unsigned)((t0 - lane) & (kPRing - 1));
+        }
+#endif
         // ---- sequence words of the next group
         if constexpr (!PROF) {
 #pragma unroll
@@ -788,8 +837,10 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 #endif
         S.gout += kGroup;
         if constexpr (PROF) {
+#if !SWB_PROF_SMEM
 #pragma unroll
             for (int q = 0; q < kR; ++q) S.pg[q] += kGroup;
+#endif
         } else {
 #pragma unroll
             for (int i = 0; i < kGroup; ++i) cur[i] = nxt[i];
@@ -1070,16 +1121,49 @@ __device__ __forceinline__ void loader_band(const int4* src, const int nblocks, 
     }
 }
 
+// ---------------------------------------------------------------------------------
+// feeder warp (SWB_PROF_SMEM): keeps the window of the score profile that the band's strips
+// are working on in the shared-memory ring -- blocks [lagging strip's t0 - 32, ... + kPRing) of the
+// letter rows in use -- and publishes the number of blocks staged
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void feeder_band(const FillParams& p, int4* ring, const int lane, const int wpc,
+                                            volatile int* progress, volatile int* fed_flag, const int end)
+{
+    const int nl = *p.nletters;
+    const int nrows = nl + 1;                       // the letters of b and the row that never matches
+    int fed = -kProfPad;                            // next block to stage (blocks -31..-1: lanes that have not started)
+    while (fed < end) {
+        int lo = 0x7fffffff;
+        for (int w = 0; w < wpc; ++w) lo = min(lo, progress[w]);
+        if (lo == 0x7fffffff) break;                // every strip of the band has finished
+        const int hi = min(end, lo - 32 + kPRing);  // slots of blocks < lo - 32 are free: lane 31 of the slowest strip is at lo - 31
+        if (fed >= hi) { __nanosleep(400); continue; }
+        const int nb = hi - fed;
+        for (int it = lane; it < nb * nrows; it += 32) {
+            const int r = it / nb, j = fed + (it - r * nb);
+            const int row = (r == nl) ? kMaxLetters : r;
+            const int4 v = __ldg(p.prof + (long long)row * p.prof_stride + kProfPad + j);
+            const int slot = j & (kPRing - 1);
+            sts_volatile_int4(ring + row * kPRowInt4 + slot, v);
+            if (slot < kPMirror) sts_volatile_int4(ring + row * kPRowInt4 + kPRing + slot, v);
+        }
+        __syncwarp();
+        fed = hi;
+        if (lane == 0) *fed_flag = fed;
+    }
+}
+
 // threads per block for wpc strips per band: rows of 4 warps; the 4-wpc serving schedulers
-// hold wpc*kWriters writers (none in score-only mode) + 1 loader
+// hold wpc*kWriters writers (none in score-only mode) + the loader + the profile feeder
 __host__ __device__ constexpr int fill_block_threads(int wpc, bool store)
 {
-    return 32 * 4 * (((store ? wpc * kWriters : 0) + 1 + (4 - wpc) - 1) / (4 - wpc));
+    return 32 * 4 * (((store ? wpc * kWriters : 0) + 1 + SWB_PROF_SMEM + (4 - wpc) - 1) / (4 - wpc));
 }
 __host__ __device__ constexpr size_t fill_smem_bytes(int wpc, int KT, bool store)
 {
     return (size_t)wpc * ((store ? (size_t)kStripRows * 4 * KT * sizeof(int) + kWriters * 48 * sizeof(int4) : 0) +
-                          kRing * sizeof(int4));
+                          kRing * sizeof(int4)) +
+           (SWB_PROF_SMEM ? (size_t)kProfRows * kPRowInt4 * sizeof(int4) : 0);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1093,10 +1177,15 @@ __global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true), (KT == 64 &
 fill_kernel(const FillParams p_in)
 {
     // both instantiations are launched; the alphabet of b (counted on the device by profile_kernel) decides which runs
+#ifdef SWB_X_FORCE_COMPARE                                     // developer build: always the character-compare instantiation
+    if (PROF) return;
+#else
     if ((*p_in.nletters <= kMaxLetters) != PROF) return;
+#endif
     extern __shared__ __align__(1024) int4 smem4[];
     __shared__ int s_band;
     __shared__ int s_staged[kMaxWpc], s_drained[kMaxWpc * kWriters], s_consumed[kMaxWpc + 1];
+    __shared__ int s_progress[kMaxWpc], s_fed;     // profile ring: first step of each strip's current group / blocks staged
 
     const int lane = threadIdx.x & 31;
     const int wid  = threadIdx.x >> 5;
@@ -1111,6 +1200,7 @@ fill_kernel(const FillParams p_in)
     if (threadIdx.x < kMaxWpc) s_staged[threadIdx.x] = 0;
     if (threadIdx.x < kMaxWpc * kWriters) s_drained[threadIdx.x] = 0;
     if (threadIdx.x <= kMaxWpc) s_consumed[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_fed = -(1 << 30);
     __syncthreads();
     const int sched = ((wid & 3) + 4 - ((s_band * wpc) & 3)) & 3, wrow = wid >> 2;
     const int nserv = 4 - wpc;                                   // schedulers that serve writers / loader
@@ -1122,11 +1212,13 @@ fill_kernel(const FillParams p_in)
         const int slot = wrow * nserv + (sched - wpc);
         if (slot < nwriters) { role = 1; w = slot; }
         else if (slot == nwriters) role = 2;
+        else if (slot == nwriters + 1 && PROF && SWB_PROF_SMEM) role = 3;
     }
 
     int4* stage4  = smem4;                                       // [wpc][kStripRows][KT]   (STORE only)
     int4* rings   = stage4 + (STORE ? (size_t)wpc * kStripRows * KT : 0);   // [wpc][kRing]
     int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc*kWriters][48]      (STORE only)
+    int4* pring   = rowtabs + (STORE ? (size_t)wpc * kWriters * 48 : 0);   // [kProfRows][kPRowInt4]  (SWB_PROF_SMEM)
 
     for (int i = threadIdx.x; i < wpc * kRing; i += blockDim.x) rings[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
@@ -1143,6 +1235,9 @@ fill_kernel(const FillParams p_in)
     p.gmax += pair;
     if (!STORE) p.row_best += pair * (p.n + 1);
     const long long band_r0 = 1 + (long long)band * wpc * kStripRows;
+    if (threadIdx.x < kMaxWpc)
+        s_progress[threadIdx.x] = (threadIdx.x < wpc && band_r0 + (long long)kStripRows * threadIdx.x <= p.n) ? 0 : 0x7fffffff;
+    __syncthreads();
 
     if (role == 0) {
         // ------------------------------------------------ compute
@@ -1159,6 +1254,7 @@ fill_kernel(const FillParams p_in)
             if constexpr (PROF) {
                 const int li = (row <= p.n) ? (int)p.lmap[p.b[row - 1]] : kMaxLetters;
                 S.pg[q] = p.prof + (long long)li * p.prof_stride + kProfPad - lane;      // block -lane of step 0
+                S.rb[q] = (unsigned)__cvta_generic_to_shared(pring + (size_t)li * kPRowInt4);
             }
         }
         S.one = opaque(1);
@@ -1219,7 +1315,9 @@ fill_kernel(const FillParams p_in)
         compute_strip<KT, STORE, PROF>(p, S, aw, (unsigned)__cvta_generic_to_shared(s_staged + w),
                       (unsigned)__cvta_generic_to_shared(s_drained + w * kWriters),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w),
-                      (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, strip + pair * p.nstrips);
+                      (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, strip + pair * p.nstrips,
+                      (unsigned)__cvta_generic_to_shared(s_progress + w), (unsigned)__cvta_generic_to_shared(&s_fed));
+        if (PROF && SWB_PROF_SMEM && lane == 0) *(volatile int*)(s_progress + w) = 0x7fffffff;    // the feeder may stop minding me
         if (STORE && SWB_KMAXC) {
             // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel).  The rows past n of a
             // partial strip never match (inv), so their cells stay below the cells above them.
@@ -1252,6 +1350,10 @@ fill_kernel(const FillParams p_in)
         // ------------------------------------------------ loader
         if (band == 0 || band_r0 > p.n) return;
         loader_band(p.boundary + (size_t)(band - 1) * p.bstride + kBoundaryPad, p.jmax + 1, rings, lane, s_consumed);
+    } else if (role == 3) {
+        // ------------------------------------------------ profile feeder
+        if (band_r0 > p.n) return;
+        feeder_band(p, pring, lane, wpc, s_progress, &s_fed, p.ngroups * kGroup + 16);
     }
 }
 

@@ -86,3 +86,37 @@ def test_shard_pairs_partition(swb):
         assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
     with pytest.raises(swb.SwbError):
         swb.shard_pairs(10, 0, 0)
+
+
+def test_cigar_and_alignment_strings(swb, oracle):
+    """Host helpers of the alignment emission against a walk of the oracle's P (omp_smithW.c:405-420)."""
+    import numpy as np
+    a, b = b"TGTTACGG", b"GGTTGACTA"                      # the built-in case: path 69 -> 59 -> 49 -> 40 -> 30 -> 20
+    H, P, mp = oracle.fill(a, b, order="wavefront")
+    m = len(a)
+    moves, pos = bytearray(), mp
+    while P.reshape(-1)[pos] != 0:
+        code = int(P.reshape(-1)[pos]); moves.append(code)
+        pos -= {3: m + 2, 1: m + 1, 2: 1}[code]
+    assert len(moves) == 6
+    cig = swb.cigar_from_moves(bytes(moves))
+    ga, gb = swb.alignment_from_moves(bytes(moves), a, b, mp, m + 1)
+    assert cig == "3M1I2M" and (ga, gb) == (b"GTT-AC", b"GTTGAC")
+    # random pair: the gapped strings spell the two subsequences and their column scores add up to H[maxPos]
+    rng = np.random.default_rng(3)
+    a = rng.choice(np.frombuffer(b"ACGT", np.uint8), 300).tobytes(); b = rng.choice(np.frombuffer(b"ACGT", np.uint8), 260).tobytes()
+    H, P, mp = oracle.fill(a, b, order="wavefront")
+    m = len(a); moves, pos = bytearray(), mp
+    while P.reshape(-1)[pos] != 0:
+        code = int(P.reshape(-1)[pos]); moves.append(code)
+        pos -= {3: m + 2, 1: m + 1, 2: 1}[code]
+    ga, gb = swb.alignment_from_moves(bytes(moves), a, b, mp, m + 1)
+    i1, j1 = divmod(mp, m + 1); i0, j0 = divmod(pos, m + 1)
+    assert ga.replace(b"-", b"") == a[j0:j1] and gb.replace(b"-", b"") == b[i0:i1]
+    score = sum(-2 if (x == 45 or y == 45) else (3 if x == y else -3) for x, y in zip(ga, gb))
+    assert score == H.reshape(-1)[mp]
+    cig = swb.cigar_from_moves(bytes(moves))
+    import re
+    ops = re.findall(r"(\d+)([MID])", cig)
+    assert sum(int(n) for n, _ in ops) == len(moves)
+    assert sum(int(n) for n, o in ops if o in "MD") == j1 - j0 and sum(int(n) for n, o in ops if o in "MI") == i1 - i0
