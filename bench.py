@@ -336,13 +336,13 @@ def secondary_single_gpu(swb, torch, dev, local, peak):
         cells = (r + 1) * (c + 1)
         dH = torch.empty(cells, dtype=torch.int32, device=dev); dP = torch.empty(cells, dtype=torch.int32, device=dev)
         ms = best_of(lambda: swb.fill_async(a_d, c, b_d, r, dH, dP, c + 1, d_pos, d_sc, device=local, stream=stream, timer=timer))
-        nstrips = (r + 63) // 64
+        nstrips = (r + 95) // 96                             # single pairs: strips of 96 rows (32 lanes x 3 rows)
         steps_chain = nstrips * 40 + (c // 4 + 32)           # strips x (32 lanes + poll granularity) + one strip's sweep
         out[f"skewed_{c}x{r}"] = {"workload": f"{c} cols x {r} rows full fill", "kernel_ms": ms, "gcups": c * r / ms / 1e6,
                                   "hbm_frac": 8.0 * cells / ms / 1e6 / peak, "maxPos": int(d_pos.item()),
                                   "latency_bound": {"chain_steps": steps_chain, "t_step_ns": ms * 1e6 / steps_chain,
-                                                    "what": "strips*(32+8) + cols/4+32 dependent steps; t_step = kernel time / chain steps "
-                                                            "(the in-situ cost of one 2x4-cell step when the chain is the only limiter)"}}
+                                                    "what": "strips*(32+8) + cols/4+32 dependent steps (96-row strips); t_step = kernel time / chain steps "
+                                                            "(the in-situ cost of one 3x4-cell step when the chain is the only limiter)"}}
         del dH, dP
     # batch: 65536 x 256x256 in one launch (BASELINE configs[4]); sharded pair-wise when N > 1
     out["batch"] = batch_record(swb, torch, dev, local, peak, 0, 65536)

@@ -1,8 +1,16 @@
 // swb_api.cu -- thin C ABI over the sm_100a kernels (include/swb200.h).
 // Host code is plain C++/CUDA runtime; no torch types, no CPU fallback.
 #include "../../include/swb200.h"
-#include "swb_kernels.cuh"
+#include "swb_kernels.cuh"              // namespace swb: two rows per lane (batches, score-only) + backtrack, argmax ...
 #include "swb_backtrack.cuh"
+#undef SWB_NS
+#undef SWB_ROWS_PER_LANE
+#define SWB_NS swb_tall
+#define SWB_ROWS_PER_LANE 3
+#define SWB_FILL_ONLY 1
+#include "swb_kernels.cuh"              // namespace swb_tall: three rows per lane (single large pairs)
+#undef SWB_NS
+#undef SWB_FILL_ONLY
 
 #include <algorithm>
 #include <cstdio>
@@ -70,18 +78,6 @@ int check_scoring(const swb_scoring& sc, int64_t m, int64_t n)
 struct swb_timer { cudaEvent_t start = nullptr, stop = nullptr; int device = 0; };
 namespace {
 
-struct Workspace {
-    // one stream-ordered allocation, carved up
-    unsigned char* base = nullptr;
-    unsigned* a4 = nullptr; long long a4_words = 0;
-    unsigned char* a_dev = nullptr; unsigned char* b_dev = nullptr;
-    int* ticket = nullptr; int* gmax = nullptr; unsigned long long* key = nullptr;
-    int* strip_max = nullptr;
-    int4* boundary = nullptr; long long bstride = 0;
-    unsigned long long* row_best = nullptr;
-    int4* prof = nullptr; long long prof_stride = 0, prof_pair_stride = 0;
-};
-
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // The workspace comes from a stream-ordered pool on every call.  The library owns one PRIVATE pool per device
@@ -113,197 +109,39 @@ cudaMemPool_t workspace_pool(int device)
     return g_pools[device];
 }
 
-int pick_wpc(int64_t n, int64_t npairs, int kt, bool store, const swb_tuning* tuning)
-{
-    int wpc = (npairs > 1) ? 1 : 2;         // measured: 65536 x 256x256 pairs 295 vs 247 GCUPS with 1 strip per CTA
-#ifdef SWB_DEV_KNOBS
-    if (const char* e = std::getenv("SWB_WPC")) wpc = std::atoi(e);
-#endif
-    if (tuning && tuning->warps_per_band > 0) wpc = tuning->warps_per_band;
-    wpc = std::max(1, std::min(wpc, swb::kMaxWpc));
-    while (wpc > 1 && swb::fill_smem_bytes(wpc, kt, store) + 2048 > 227 * 1024) --wpc;     // 227 KB of shared memory per CTA on sm_100
-    const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
-    if (strips < wpc) wpc = (int)strips;
-    return wpc;
-}
-
-template <int KT, bool STORE, bool PROF>
-cudaError_t launch_fill_one(const swb::FillParams& p, long long nblocks, int wpc, cudaStream_t st)
-{
-    // score-only needs 1 KB per strip but asks for the full-fill footprint of a large pair: one CTA per SM
-    // keeps waiting CTAs off the schedulers of the working ones (measured 13 ms -> see DESIGN.md)
-    const size_t smem = (!STORE && p.nbands > 8) ? swb::fill_smem_bytes(wpc, 64, true) : swb::fill_smem_bytes(wpc, KT, STORE);
-    cudaError_t e = cudaFuncSetAttribute(swb::fill_kernel<KT, STORE, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    swb::fill_kernel<KT, STORE, PROF><<<(unsigned)nblocks, swb::fill_block_threads(wpc, STORE), smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-// Both instantiations are enqueued: the one that does not match the alphabet of b (counted on the device, so that the
-// call stays asynchronous for device-resident sequences) returns at once.
-template <int KT, bool STORE>
-cudaError_t launch_fill(const swb::FillParams& p, long long nblocks, int wpc, cudaStream_t st)
-{
-    cudaError_t e = launch_fill_one<KT, STORE, true>(p, nblocks, wpc, st);
-    if (e != cudaSuccess) return e;
-    return launch_fill_one<KT, STORE, false>(p, nblocks, wpc, st);
-}
-
-// The one implementation behind swb_fill_async, swb_fill_batch_async and swb_score_only_async.
-//   npairs equally shaped pairs: a = npairs*m bytes, b = npairs*n bytes, pair k's matrices at
-//   dH/dP + k*pair_stride; d_maxPos / d_maxScore hold npairs entries.  store == false: score only.
 struct StripLink {                         // column-strip mode (nullptr members = not used)
     const int32_t* left_in = nullptr; const int* left_flags = nullptr;
     int32_t* right_out = nullptr; int* right_flags = nullptr; int epoch = 0;
 };
 
+}  // namespace
+
+// The fill's host side, once per kernel geometry (see swb_fill_impl.inc)
+namespace swb {
+#include "swb_fill_impl.inc"
+}
+namespace swb_tall {
+#define SWB_SINGLE_ONLY 1
+#include "swb_fill_impl.inc"
+#undef SWB_SINGLE_ONLY
+}
+
+namespace {
+// The one implementation behind swb_fill_async, swb_fill_batch_async and swb_score_only_async.
+//   npairs equally shaped pairs: a = npairs*m bytes, b = npairs*n bytes, pair k's matrices at
+//   dH/dP + k*pair_stride; d_maxPos / d_maxScore hold npairs entries.  store == false: score only.
+// Single pairs with H/P stores run the three-rows-per-lane geometry (96-row strips: a third fewer links in the
+// strip-to-strip chain that bounds large fills); batches and score-only keep two rows per lane (two CTAs per SM).
 int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs, const swb_scoring* scoring,
               int32_t* dH, int32_t* dP, int64_t pitch, int64_t pair_stride, int64_t* d_maxPos, int32_t* d_maxScore,
               int device, void* stream, const swb_tuning* tuning, bool store, const StripLink* link = nullptr)
 {
-    if (!a || !b || m <= 0 || n <= 0 || npairs <= 0) return SWB_ERR_ARG;
-    if (store && (!dH || !dP || pitch < m + 1)) return SWB_ERR_ARG;
-    if (store && npairs > 1 && pair_stride < (n + 1) * pitch) return SWB_ERR_ARG;
-    if (m >= (1LL << 30) || n >= (1LL << 30)) return SWB_ERR_RANGE;
-    if (store && pitch >= (1LL << 23)) return SWB_ERR_RANGE;      // the writers address a strip with 32-bit byte offsets (64 rows * pitch * 4)
-    if (store && ((reinterpret_cast<uintptr_t>(dH) & 15) || (reinterpret_cast<uintptr_t>(dP) & 15))) return SWB_ERR_ALIGN;
-    const swb_scoring sc = scoring ? *scoring : kDefaultScoring;
-    // (column-strip mode: m is the LOCAL width; the scores are bounded by the whole pair's min(m_total, n) <= n)
-    if (int rc = check_scoring(sc, link ? n : m, n)) return rc;
-    if (!store) pitch = m + 1;
-
-    DeviceGuard guard(device);
-    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-
-    // single large pairs: deep staging ring, one CTA per SM; batches of small pairs: shallow ring, more CTAs per SM
-    int kt = (npairs > 1) ? 32 : 64;
-#ifdef SWB_DEV_KNOBS
-    if (const char* e = std::getenv("SWB_KT")) kt = (std::atoi(e) == 32) ? 32 : 64;     // developer knob
-#endif
-    const int wpc = pick_wpc(n, npairs, kt, store, tuning);
-    const int64_t strips = (n + swb::kStripRows - 1) / swb::kStripRows;
-    const int nbands = (int)((strips + wpc - 1) / wpc);
-    if ((long long)nbands * npairs >= (1LL << 31)) return SWB_ERR_RANGE;
-    const int jmax = (int)(m >> 2);                                   // last block with a valid column
-    const int ngroups = (jmax + 1 + 31 + swb::kGroup - 1) / swb::kGroup;
-
-    // ---- workspace (stream ordered)
-    Workspace ws;
-    ws.a4_words = swb::kAPad + (long long)ngroups * swb::kGroup + 16;
-    ws.bstride = (long long)ngroups * swb::kGroup + swb::kBoundaryPad;
-    const bool a_on_dev = is_device_ptr(a), b_on_dev = is_device_ptr(b);
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_a4 = carve((size_t)npairs * ws.a4_words * sizeof(unsigned));
-    const size_t o_a = carve(a_on_dev ? 0 : (size_t)(m * npairs));
-    const size_t o_b = carve(b_on_dev ? 0 : (size_t)(n * npairs));
-    const size_t o_small = carve(2048);           // ticket, NUL flag, letter count | present[256] | lmap[256]
-    ws.prof_stride = swb::kProfPad + (long long)ngroups * swb::kGroup + 16;
-    ws.prof_pair_stride = ws.prof_stride * swb::kProfRows;
-    const size_t o_prof = carve((size_t)npairs * (size_t)ws.prof_pair_stride * sizeof(int4));
-    const size_t o_gmax = carve((size_t)npairs * sizeof(int));
-    const size_t o_key = carve((size_t)npairs * sizeof(unsigned long long));
-    const size_t o_smax = carve((size_t)(strips * npairs) * sizeof(int));
-    const size_t boundary_bytes = (size_t)npairs * (size_t)std::max(nbands - 1, 0) * (size_t)ws.bstride * sizeof(int4);
-    const size_t o_bnd = carve(boundary_bytes);
-    const size_t o_rb = carve(store ? 0 : (size_t)npairs * (size_t)(n + 1) * sizeof(unsigned long long));
-    if (cudaMemPool_t pool = workspace_pool(device)) SWB_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&ws.base), off, pool, st));
-    else                                             SWB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws.base), off, st));
-    ws.a4 = reinterpret_cast<unsigned*>(ws.base + o_a4);
-    ws.a_dev = ws.base + o_a; ws.b_dev = ws.base + o_b;
-    ws.ticket = reinterpret_cast<int*>(ws.base + o_small);
-    ws.gmax = reinterpret_cast<int*>(ws.base + o_gmax);
-    ws.key = reinterpret_cast<unsigned long long*>(ws.base + o_key);
-    ws.strip_max = reinterpret_cast<int*>(ws.base + o_smax);
-    ws.boundary = reinterpret_cast<int4*>(ws.base + o_bnd);
-    ws.row_best = reinterpret_cast<unsigned long long*>(ws.base + o_rb);
-    ws.prof = reinterpret_cast<int4*>(ws.base + o_prof);
-    int* const d_nletters = ws.ticket + 2;
-    int* const d_present = ws.ticket + 64;
-    unsigned char* const d_lmap = reinterpret_cast<unsigned char*>(ws.ticket + 64 + 256);
-
-    int rc = SWB_OK;
-    auto run = [&]() -> int {
-        const unsigned char* a_d = reinterpret_cast<const unsigned char*>(a);
-        const unsigned char* b_d = reinterpret_cast<const unsigned char*>(b);
-        if (!a_on_dev) { SWB_CUDA(cudaMemcpyAsync(ws.a_dev, a, (size_t)(m * npairs), cudaMemcpyHostToDevice, st)); a_d = ws.a_dev; }
-        if (!b_on_dev) { SWB_CUDA(cudaMemcpyAsync(ws.b_dev, b, (size_t)(n * npairs), cudaMemcpyHostToDevice, st)); b_d = ws.b_dev; }
-        if (store) {
-            // row 0 of H and P (the reference gets it from calloc, omp_smithW.c:113-118)
-            if (npairs == 1) {
-                SWB_CUDA(cudaMemsetAsync(dH, 0, (size_t)(m + 1) * sizeof(int32_t), st));
-                SWB_CUDA(cudaMemsetAsync(dP, 0, (size_t)(m + 1) * sizeof(int32_t), st));
-            } else {
-                SWB_CUDA(cudaMemset2DAsync(dH, (size_t)pair_stride * sizeof(int32_t), 0, (size_t)(m + 1) * sizeof(int32_t), (size_t)npairs, st));
-                SWB_CUDA(cudaMemset2DAsync(dP, (size_t)pair_stride * sizeof(int32_t), 0, (size_t)(m + 1) * sizeof(int32_t), (size_t)npairs, st));
-            }
-        }
-        // band-boundary rows carry their validity tag in the data: clear the tags
-        if (boundary_bytes) SWB_CUDA(cudaMemsetAsync(ws.boundary, 0, boundary_bytes, st));
-        SWB_CUDA(cudaMemsetAsync(ws.ticket, 0, 2048, st));           // ticket, NUL flag, alphabet of b
-        const int prep_blocks = (int)std::min<int64_t>((ws.a4_words * npairs + 255) / 256, 1184);
-        swb::prep_kernel<<<prep_blocks, 256, 0, st>>>(a_d, m, npairs, ws.a4, ws.a4_words, ws.ticket, ws.gmax, ws.key,
-                                                      ws.strip_max, (long long)(strips * npairs), b_d, (long long)(n * npairs),
-                                                      ws.ticket + 1, d_present);
-        SWB_CUDA(cudaGetLastError());
-        {
-            const int64_t items = ws.prof_pair_stride * npairs;
-            const int pblocks = (int)std::min<int64_t>((items + 255) / 256, 1184);
-            swb::profile_kernel<<<pblocks, 256, 0, st>>>(a_d, m, npairs, d_present, d_lmap, d_nletters, ws.prof, ws.prof_stride,
-                                                         ws.prof_pair_stride, 16 * sc.match + swb::kTieDiag,
-                                                         16 * sc.mismatch + swb::kTieDiag);
-            SWB_CUDA(cudaGetLastError());
-        }
-
-        swb::FillParams p{};
-        p.a4 = ws.a4; p.b = b_d;
-        p.H = dH; p.P = dP; p.pitch = pitch; p.m = m; p.n = n;
-        p.s_match = 16 * sc.match + swb::kTieDiag;
-        p.s_mismatch = 16 * sc.mismatch + swb::kTieDiag;
-        p.g_up = 16 * sc.gap + swb::kTieUp;
-        p.g_left = 16 * sc.gap + swb::kTieLeft;
-        p.ngroups = ngroups; p.jmax = jmax; p.wpc = wpc;
-        p.boundary = ws.boundary; p.bstride = ws.bstride;
-        p.ticket = ws.ticket; p.nul_flag = ws.ticket + 1; p.strip_max = ws.strip_max; p.gmax = ws.gmax;
-        p.trace = tuning ? reinterpret_cast<unsigned long long*>(tuning->trace) : nullptr;
-        p.nbands = nbands; p.nstrips = strips; p.a4_stride = ws.a4_words; p.pair_stride = pair_stride;
-        p.row_best = ws.row_best;
-        p.prof = ws.prof; p.prof_stride = ws.prof_stride; p.prof_pair_stride = ws.prof_pair_stride;
-        p.lmap = d_lmap; p.nletters = d_nletters;
-        if (link) { p.left_in = link->left_in; p.left_flags = link->left_flags; p.right_out = link->right_out;
-                    p.right_flags = link->right_flags; p.epoch = link->epoch; }
-        swb_timer* timer = tuning ? tuning->timer : nullptr;
-        if (timer) SWB_CUDA(cudaEventRecord(timer->start, st));
-        const long long nblocks = (long long)nbands * npairs;
-        cudaError_t e;
-        if (!store)        e = launch_fill<64, false>(p, nblocks, wpc, st);
-        else if (kt == 64) e = launch_fill<64, true>(p, nblocks, wpc, st);
-        else               e = launch_fill<32, true>(p, nblocks, wpc, st);
-        if (e != cudaSuccess) return cuda_fail(e, "fill_kernel launch", __LINE__);
-        if (timer) SWB_CUDA(cudaEventRecord(timer->stop, st));
-
-        if (store) {
-            const int am_blocks = (npairs > 1) ? 1 : (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
-            swb::argmax_kernel<<<dim3((unsigned)npairs, (unsigned)am_blocks), 256, 0, st>>>(dH, pitch, pair_stride, m, n, ws.strip_max,
-                                                                                              ws.gmax, ws.key);
-            SWB_CUDA(cudaGetLastError());
-            swb::finalize_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(ws.key, ws.gmax, pitch, npairs,
-                                                                                   reinterpret_cast<long long*>(d_maxPos), d_maxScore);
-            SWB_CUDA(cudaGetLastError());
-        } else {
-            swb::rowbest_argmax_kernel<<<(unsigned)npairs, 256, 0, st>>>(ws.row_best, n, pitch, ws.gmax,
-                                                                        reinterpret_cast<long long*>(d_maxPos), d_maxScore);
-            SWB_CUDA(cudaGetLastError());
-        }
-        return SWB_OK;
-    };
-    rc = run();
-    cudaError_t fe = cudaFreeAsync(ws.base, st);
-    if (rc == SWB_OK && fe != cudaSuccess) rc = cuda_fail(fe, "cudaFreeAsync", __LINE__);
-    return rc;
+    if (store && npairs == 1)
+        return swb_tall::fill_impl(a, m, b, n, npairs, scoring, dH, dP, pitch, pair_stride, d_maxPos, d_maxScore, device, stream,
+                                   tuning, store, link);
+    return swb::fill_impl(a, m, b, n, npairs, scoring, dH, dP, pitch, pair_stride, d_maxPos, d_maxScore, device, stream,
+                          tuning, store, link);
 }
-
 }  // namespace
 
 extern "C" {

@@ -44,7 +44,8 @@
 //  * maxPos: a second tiny kernel scans only the strips that attain the global maximum,
 //    with the reference's tie-break (first in anti-diagonal order, bottom-left to
 //    top-right; omp_smithW.c:203-215,384-387).
-#pragma once
+// This header is included twice by swb_api.cu: as namespace swb (two rows per lane: batches, score-only) and as
+// namespace swb_tall (three rows per lane: single large pairs) -- SWB_NS / SWB_ROWS_PER_LANE / SWB_FILL_ONLY select.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -63,8 +64,14 @@
 #define SWB_X_WRITERSLEEP 64
 #endif
 
+#ifndef SWB_STAGE_LATE
+#define SWB_STAGE_LATE 0               // 1: the staging stores of a step are issued after its shuffles
+#endif
 #ifndef SWB_ST_MODE
 #define SWB_ST_MODE 0
+#endif
+#ifdef SWB_ST
+#undef SWB_ST
 #endif
 #if SWB_ST_MODE == 0
 #define SWB_ST(p, v) __stcs(p, v)
@@ -76,15 +83,10 @@
 #define SWB_ST(p, v) __stwt(p, v)
 #endif
 
-#ifndef SWB_PROF_SMEM
-#define SWB_PROF_SMEM 1                // 1: the score profile is staged in a shared-memory ring by a feeder warp (one conflict-free
-                                       //    LDS.128 per row and step); 0: every lane loads its rows from global memory / L1
+#ifndef SWB_NS
+#define SWB_NS swb
 #endif
-#ifndef SWB_PROF_PREFETCH
-#define SWB_PROF_PREFETCH 40           // SWB_PROF_SMEM == 0: blocks ahead of the current step that are prefetched into L1 (0 = off)
-#endif
-
-namespace swb {
+namespace SWB_NS {
 
 #ifndef SWB_ROWS_PER_LANE
 #define SWB_ROWS_PER_LANE 2
@@ -100,7 +102,11 @@ constexpr int kWriters  = kStripRows / kWRows;     // writer warps per strip
 // matrix -- 12.3 ms against 5.1 ms for the 45000x45000 fill: bulk copies this small cost far more than the STGs.)
 // KT (template parameter of the fill kernel) = staging ring depth in steps (16-byte slots per
 // row): 64 for single large pairs, 32 for batches of small pairs (more CTAs per SM)
-constexpr int kRing     = 64;          // hand-off ring capacity in blocks (power of two)
+#ifndef SWB_RING_LOG
+#define SWB_RING_LOG 6
+#endif
+constexpr int kRingLog  = SWB_RING_LOG;
+constexpr int kRing     = 1 << kRingLog;   // hand-off ring capacity in blocks (power of two, >= 64)
 constexpr int kGroup    = 8;           // steps per synchronisation group
 #ifndef SWB_WAIT_STEPS
 #define SWB_WAIT_STEPS 4
@@ -110,24 +116,18 @@ constexpr int kWaitSteps = SWB_WAIT_STEPS;   // steps per poll of the strip abov
 #define SWB_WAIT_STEPS_SINGLE 8        // measured: 45000x45000 4.99 -> 4.89 ms, 100000x100000 18.7 -> 18.5 ms; the batch and
 #endif                                 // score-only instantiations are 2 % faster with 4
 constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
-// Score profile (PROF instantiations): when b uses at most kMaxLetters distinct byte values, the substitution scores
-// come from a table prof[letter][block] = the four keys 16*s + kTieDiag of columns 4j..4j+3 against that letter
-// (one 16-byte load per row and step, prefetched kProfDepth steps ahead) instead of being derived from the packed
-// characters with a compare and a select per cell on the compute warp's ALU pipe.  Row kMaxLetters of the table
-// never matches (rows past n of a partial strip).
-constexpr int kMaxLetters = 8;
-constexpr int kProfRows   = kMaxLetters + 1;
-constexpr int kProfPad    = 32;        // leading pad blocks of a profile row (blocks -31..-1 of a strip's first steps)
-// prefetch distance in steps (power of two, <= kGroup): 4 in the single-pair full fill (one CTA per SM, registers to
-// spare), 2 in the batch and score-only instantiations (two CTAs per SM: 80 registers)
-__host__ __device__ constexpr int prof_depth(int KT, bool STORE) { return SWB_PROF_SMEM ? 2 : ((KT == 64 && STORE) ? 4 : 2); }
-// shared-memory ring of the profile (SWB_PROF_SMEM): block j of letter row r sits in slot j & (kPRing - 1) of row r; the
-// first kPMirror slots are mirrored behind the ring so that the kGroup + depth loads of one group never wrap (their
-// offsets from the group's first slot are immediates).  The window a band needs is [lagging strip's block - 31,
-// leading strip's block + 8 + depth]; the hand-off credits keep the strips of a band within 88 steps of each other.
-constexpr int kPRing   = 256;
-constexpr int kPMirror = 16;
-constexpr int kPRowInt4 = kPRing + kPMirror;
+// Score look-up (PROF instantiations): when b uses at most kMaxLetters distinct byte values and the scores fit a signed
+// byte, the substitution scores are not derived from the characters with a compare and a select per cell.  The packed
+// copy of a then holds, per block of four columns, one SELECTOR word: nibble e = the rank of column e's character among
+// the letters of b (kPadCode for positions outside the sequence and for characters that do not occur in b).  Every lane
+// keeps, for each of its rows, the eight score bytes of that row's character against the eight codes (two registers);
+// ONE byte permute (PRMT) with the selector yields the row's four score bytes of a step, and the diagonal candidate of a
+// cell is ONE dot-product instruction, kd = dp4a(scores, 16 << 8e, 16*H_diag + 7): IDP.4A issues on the FMA pipe
+// (measured: tools/ubench_dp4a.cu), next to the IMAD that forms the UP candidate, so that the ALU pipe sees three
+// instructions per cell (two three-input maxima and the mask) instead of 6.5.  H is carried as 16*H + kH7 in these
+// instantiations: the tie code of the diagonal candidate then comes with the operand.
+constexpr int kMaxLetters = 7;
+constexpr int kPadCode    = 7;
 constexpr int kBoundaryPad = 32;       // spare blocks in front of a band-boundary row (blocks -31..-1 of a strip's first steps)
 constexpr int kMaxWpc   = 2;           // strips per band (CTA) upper bound: compute warps on schedulers 0..wpc-1,
                                        // writers + loader on the others
@@ -165,13 +165,12 @@ struct FillParams {
     long long       bstride;
     int*            ticket;                // band ticket counter
     const int*      nul_flag;              // != 0: b holds a NUL byte (it would match the zero padding of a: see prep_kernel)
-    // score profile (see kMaxLetters): pair k uses prof + k*prof_pair_stride; the table and the letter map are
-    // shared by all pairs of a batch only through their layout, not their contents
-    const int4*     prof;                  // [kProfRows][prof_stride] per pair
-    long long       prof_stride, prof_pair_stride;
-    const unsigned char* lmap;             // [256] byte value -> profile row (letters of b over ALL pairs)
+    // score look-up (see kMaxLetters)
+    const unsigned char* lmap;             // [256] byte value -> its rank among the letters of b (all pairs), kPadCode if none
     const int*      nletters;              // distinct byte values in b; > kMaxLetters: the PROF instantiation returns at once,
                                            // <= kMaxLetters: the character-compare instantiation does
+    int             match8, mismatch8;     // the raw scores (they fit a signed byte when prof_ok)
+    int             prof_ok;               // host: the scores fit a byte (else the character-compare instantiation runs)
     int*            strip_max;             // [nstrips] max H of each strip (atomicMax by its writers)
     int*            gmax;                  // global max H
     unsigned long long* trace;             // optional [nstrips][8] globaltimer stamps (developer tool) or nullptr
@@ -287,7 +286,7 @@ __device__ __forceinline__ void spin_until_ge(unsigned a, int want)
 __device__ __forceinline__ void wait_block(unsigned ring_in, int x)
 {
     const unsigned a = ring_in + 16u * (unsigned)((x + 32) & (kRing - 1));
-    const int want = 1 + (((x + 32) >> 6) & 1);
+    const int want = 1 + (((x + 32) >> kRingLog) & 1);
     // Pure spin: __nanosleep oversleeps by microseconds on this hardware whatever its argument.  With a
     // `nanosleep(20)` after 64 polls here a strip that followed its producer closely fell into a mode of one sleep
     // per run of steps (1400 clk per step instead of 250) and dragged every later strip with it: score-only launches
@@ -349,56 +348,49 @@ __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m, lo
 }
 
 // ---------------------------------------------------------------------------------
-// score profile (matchMissmatchScore, omp_smithW.c:394-399, tabulated per letter of b): every block first ranks
-// the byte values that occur in b (present[], set by prep_kernel); block 0 publishes the map and the count.  With
-// at most kMaxLetters letters, row r of the table holds for every block j the keys 16*s + kTieDiag of columns
-// 4j..4j+3 (column c reads a[c-1]) against letter r; positions outside the sequence and the row kMaxLetters
-// never match.
+// score look-up (matchMissmatchScore, omp_smithW.c:394-399): ranks the byte values that occur in b (present[], set by
+// prep_kernel; block 0 publishes the map and the count) and, with at most kMaxLetters of them, rewrites the packed copy
+// of a as selector words -- nibble e of word kAPad+j = rank of a[4j+e-1], kPadCode outside the sequence or for a
+// character that b does not use (it matches no row).
 // ---------------------------------------------------------------------------------
-__global__ void profile_kernel(const unsigned char* __restrict__ a, long long m, long long npairs,
-                               const int* __restrict__ present, unsigned char* lmap, int* nletters,
-                               int4* __restrict__ prof, long long prof_stride, long long prof_pair_stride,
-                               int s_match, int s_mismatch)
+__global__ void selector_kernel(const unsigned char* __restrict__ a, long long m, long long npairs,
+                                const int* __restrict__ present, unsigned char* lmap, int* nletters,
+                                unsigned* __restrict__ a4, long long nwords)
 {
-    __shared__ unsigned char s_letter[kProfRows];
+    __shared__ unsigned char s_map[256];
     __shared__ int s_cnt[8];
     __shared__ int s_n;
     {
         // rank of byte value c among the present ones (256 threads = one per value)
         const int c = threadIdx.x;
-        const bool on = c < 256 && present[c] != 0;
+        const bool on = present[c] != 0;
         const unsigned bal = __ballot_sync(0xffffffffu, on);
-        if ((c & 31) == 0 && c < 256) s_cnt[c >> 5] = __popc(bal);
+        if ((c & 31) == 0) s_cnt[c >> 5] = __popc(bal);
         __syncthreads();
         int before = 0, total = 0;
         for (int w = 0; w < 8; ++w) { if (w < (c >> 5)) before += s_cnt[w]; total += s_cnt[w]; }
         const int rank = before + __popc(bal & ((1u << (c & 31)) - 1u));
-        if (on && rank < kMaxLetters) s_letter[rank] = (unsigned char)c;
+        s_map[c] = (unsigned char)((on && rank < kMaxLetters) ? rank : kPadCode);
         if (c == 0) s_n = total;
-        if (blockIdx.x == 0 && c < 256) lmap[c] = (unsigned char)((on && rank < kMaxLetters) ? rank : kMaxLetters);
+        if (blockIdx.x == 0) lmap[c] = s_map[c];
         if (blockIdx.x == 0 && c == 0) *nletters = total;
         __syncthreads();
     }
-    const int nl = s_n;
-    if (nl > kMaxLetters) return;          // the table is not used: the character-compare instantiation runs
+    if (s_n > kMaxLetters) return;         // the characters stay in a4: the character-compare instantiation runs
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
-    const long long per_pair = (long long)(nl + 1) * prof_stride;
-    for (long long x = tid; x < per_pair * npairs; x += nth) {
-        const long long pair = x / per_pair, y = x % per_pair;
-        const int r = (int)(y / prof_stride);
-        const long long w = y % prof_stride;
-        const int row = (r == nl) ? kMaxLetters : r;
+    for (long long x = tid; x < nwords * npairs; x += nth) {
+        const long long pair = x / nwords, w = x % nwords;
         const unsigned char* ap = a + pair * m;
-        const long long base = 4 * (w - kProfPad) - 1;
-        int k[4];
+        const long long base = 4 * (w - kAPad) - 1;
+        unsigned word = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const long long idx = base + e;
-            const bool hit = row < kMaxLetters && idx >= 0 && idx < m && ap[idx] == s_letter[row];
-            k[e] = hit ? s_match : s_mismatch;
+            const unsigned code = (idx >= 0 && idx < m) ? (unsigned)s_map[ap[idx]] : (unsigned)kPadCode;
+            word |= code << (4 * e);
         }
-        prof[pair * prof_pair_stride + (long long)row * prof_stride + w] = make_int4(k[0], k[1], k[2], k[3]);
+        a4[x] = word;
     }
 }
 
@@ -407,6 +399,7 @@ __global__ void profile_kernel(const unsigned char* __restrict__ a, long long m,
 // ---------------------------------------------------------------------------------
 template <int KT, bool STORE, bool PROF>
 struct Strip {
+    static constexpr int kH7 = PROF ? kTieDiag : 0;      // low bits of every H-carrying register (16*H + kH7)
     static constexpr int kRowInts = 4 * KT;
     int lane;
     unsigned b4[kR];              // my rows' characters, replicated in the four bytes
@@ -431,27 +424,26 @@ struct Strip {
     int   rmax[kR], rcol[kR];     // score-only: best clean 16*H of each of my rows and its first column
     int   kmax;                   // full fill: largest key of my cells in columns 1..m (strip maximum; the writers have no
                                   // ALU slots to spare for it)
-    // PROF: score profile rows of my rows (pointer to the block of this group's first step) and the scores of the
-    // next kProfDepth steps; `one` is an opaque 1, the multiplier of the IMADs that keep the additions off the ALU pipe
-    const int4* pg[kR];
-    static constexpr int kProfDepth = prof_depth(KT, STORE);
-    int4  pf[kR][kProfDepth];
+    // PROF: the score bytes of my rows' characters against codes 0..3 / 4..7, this step's four score bytes per row,
+    // and an opaque 1 (multiplier of the IMADs that keep additions off the ALU pipe)
+    unsigned tlo[kR], thi[kR];
+    int   sb[kR];
     int   one;
-    unsigned rb[kR];              // SWB_PROF_SMEM: shared address of my rows' rows of the profile ring ...
-    unsigned rg[kR];              //                ... + the slot of this group's first step (block t0 - lane)
+    int   h7r;                    // kH7 in a register (LOP3 takes one immediate: (k & ~15) | 7 with two would be two instructions)
 
-    static __device__ __forceinline__ int4 ldg_prof(const int4* p)
-    {
-        int4 v;
-        asm("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-        return v;
-    }
     // x + y on the FMA pipe (IMAD with a register multiplier that ptxas cannot fold)
     __device__ __forceinline__ int addf(const int x, const int y) const
     {
         int d;
         asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(y));
         return d;
+    }
+    // PROF: the score bytes of the step whose selector word is `sel` (one PRMT per row)
+    __device__ __forceinline__ void lookup(const unsigned sel)
+    {
+#pragma unroll
+        for (int q = 0; q < kR; ++q)          // (prmt.b32 directly: __byte_perm masks the selector with 0x7777 first)
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sb[q]) : "r"(tlo[q]), "r"(thi[q]), "r"(sel));
     }
 
     __device__ __forceinline__ void scores(const unsigned aword)
@@ -507,54 +499,32 @@ struct Strip {
         // stale blocks that only reach columns > m.
         int4 v;
         if (MODE & 2) {
-            v = make_int4(0, 0, 0, 0);
+            v = make_int4(0, kH7, kH7, kH7);
             if (has_in && t + 1 <= jmax) v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
         } else {
             v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
-        }
-
-        // this step's scores from the profile; the slot is refilled with the scores of step t + kProfDepth
-        int4 sc[kR];
-        if constexpr (PROF) {
-#pragma unroll
-            for (int q = 0; q < kR; ++q) {
-                sc[q] = pf[q][I & (kProfDepth - 1)];
-#if SWB_PROF_SMEM
-                pf[q][I & (kProfDepth - 1)] = lds_volatile_int4<16 * (I + kProfDepth)>(rg[q]);
-#else
-                pf[q][I & (kProfDepth - 1)] = ldg_prof(pg[q] + (I + kProfDepth));
-#endif
-#if !SWB_PROF_SMEM && SWB_PROF_PREFETCH > 0
-                // the leading lane of every letter touches a new 32-byte sector of its profile row every other step:
-                // bring it into L1 well ahead of the load (an L2 hit is ~4 steps away)
-                if ((I & 1) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(pg[q] + (I + SWB_PROF_PREFETCH)));
-#endif
-            }
-            if (MODE & 1) {
-                // head of a strip in column-strip mode (see head_fix): blocks j < 0 and column 0 cannot take the
-                // diagonal, and the boundary value enters as the left neighbour of block 0
-#pragma unroll
-                for (int q = 0; q < kR; ++q) {
-                    sc[q].x = (j <= 0) ? kSNeg : sc[q].x;
-                    sc[q].y = (j < 0) ? kSNeg : sc[q].y;
-                    sc[q].z = (j < 0) ? kSNeg : sc[q].z;
-                    sc[q].w = (j < 0) ? kSNeg : sc[q].w;
-                    hl[q] = (j == 0) ? lb[q] : hl[q];
-                }
-            }
         }
 
         // K = max(left+gap|LEFT, up+gap|UP, diag+s|DIAG, 0|NONE)     (omp_smithW.c:339-381)
         int u0 = A0, u1 = A1, u2 = A2, u3 = A3, dg = dgp;
         dgp = A3;
         int n0, n1, n2, n3;
+        int kk[kR][4];
 #pragma unroll
         for (int q = 0; q < kR; ++q) {
             int t0, t1, t2, t3;
             if constexpr (PROF) {
-                // the two candidates that do not depend on this row are formed on the FMA pipe (IMAD) and folded
-                // with the NONE key by one three-input maximum: 3 ALU-pipe instructions per cell instead of 6.5
-                const int d0 = addf(dg, sc[q].x), d1 = addf(u0, sc[q].y), d2 = addf(u1, sc[q].z), d3 = addf(u2, sc[q].w);
+                // diagonal candidate: one IDP.4A per cell picks the cell's score byte, scales it by 16 and adds 16*H + 7;
+                // UP candidate: one IMAD; both on the FMA pipe.  One three-input maximum folds them with the NONE key.
+                int D0 = dg, D1 = u0, D2 = u1, D3 = u2;
+                if (MODE & 1) {
+                    // head of a strip in column-strip mode (see head_fix): blocks j < 0 and column 0 cannot take the
+                    // diagonal, and the boundary value enters as the left neighbour of block 0
+                    D0 = (j <= 0) ? kSNeg : D0; D1 = (j < 0) ? kSNeg : D1; D2 = (j < 0) ? kSNeg : D2; D3 = (j < 0) ? kSNeg : D3;
+                    hl[q] = (j == 0) ? lb[q] : hl[q];
+                }
+                const int d0 = __dp4a(sb[q], 16, D0), d1 = __dp4a(sb[q], 16 << 8, D1);
+                const int d2 = __dp4a(sb[q], 16 << 16, D2), d3 = __dp4a(sb[q], 16 << 24, D3);
                 const int v0 = addf(u0, gu), v1 = addf(u1, gu), v2 = addf(u2, gu), v3 = addf(u3, gu);
                 t0 = __vimax3_s32(d0, v0, kTieNone);
                 t1 = __vimax3_s32(d1, v1, kTieNone);
@@ -571,36 +541,19 @@ struct Strip {
                 t3 = __viaddmax_s32(u3, gu, p3);
             }
             dg = hl[q];                                  // diagonal of the next row's first cell
-#ifdef SWB_CLEAN_CHAIN
-            // the left-to-right chain carries clean 16*H values only: floor16(max(x + gl, T)) =
-            // max(x + 16*gap, floor16(T)) for x a multiple of 16, so the tie bits are masked off the chain
-            const int f0 = t0 & ~15, f1 = t1 & ~15, f2 = t2 & ~15, f3 = t3 & ~15;
-            const int h0 = __viaddmax_s32(hl[q], g16, f0);
-            if (q == kR - 1) n0 = __shfl_up_sync(0xffffffffu, h0, 1);
-            const int h1 = __viaddmax_s32(h0, g16, f1);
-            if (q == kR - 1) n1 = __shfl_up_sync(0xffffffffu, h1, 1);
-            const int h2 = __viaddmax_s32(h1, g16, f2);
-            if (q == kR - 1) n2 = __shfl_up_sync(0xffffffffu, h2, 1);
-            const int h3 = __viaddmax_s32(h2, g16, f3);
-            if (q == kR - 1) n3 = __shfl_up_sync(0xffffffffu, h3, 1);
+            // (PROF: H travels as 16*H + 7, one LOP3 either way)
             const int k0 = __viaddmax_s32(hl[q], gl, t0);
-            const int k1 = __viaddmax_s32(h0, gl, t1);
-            const int k2 = __viaddmax_s32(h1, gl, t2);
-            const int k3 = __viaddmax_s32(h2, gl, t3);
-#else
-            const int k0 = __viaddmax_s32(hl[q], gl, t0);
-            const int h0 = k0 & ~15;
+            const int h0 = (k0 & ~15) | h7r;
             if (q == kR - 1) n0 = __shfl_up_sync(0xffffffffu, h0, 1);
             const int k1 = __viaddmax_s32(h0, gl, t1);
-            const int h1 = k1 & ~15;
+            const int h1 = (k1 & ~15) | h7r;
             if (q == kR - 1) n1 = __shfl_up_sync(0xffffffffu, h1, 1);
             const int k2 = __viaddmax_s32(h1, gl, t2);
-            const int h2 = k2 & ~15;
+            const int h2 = (k2 & ~15) | h7r;
             if (q == kR - 1) n2 = __shfl_up_sync(0xffffffffu, h2, 1);
             const int k3 = __viaddmax_s32(h2, gl, t3);
-            const int h3 = k3 & ~15;
+            const int h3 = (k3 & ~15) | h7r;
             if (q == kR - 1) n3 = __shfl_up_sync(0xffffffffu, h3, 1);
-#endif
             hl[q] = h3;
             if (STORE && SWB_KMAXC) {
                 int e0 = k0, e1 = k1, e2 = k2, e3 = k3;
@@ -615,11 +568,15 @@ struct Strip {
                 kmax = __vimax3_s32(__vimax3_s32(kmax, e0, e1), e2, e3);
             }
             if (STORE) {
-                // stage the packed block of this row for the writers
-                if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
-                if (q == 1) sts_int4<kRowInts * 4>(sa, k0, k1, k2, k3);
-                if (q == 2) sts_int4<2 * kRowInts * 4>(sa, k0, k1, k2, k3);
-                if (q == 3) sts_int4<3 * kRowInts * 4>(sa, k0, k1, k2, k3);
+                // stage the packed block of this row for the writers (SWB_STAGE_LATE: after the last row's shuffles have
+                // been issued, so that they do not queue behind the stores in the SM's load/store pipeline)
+                if (SWB_STAGE_LATE) { kk[q][0] = k0; kk[q][1] = k1; kk[q][2] = k2; kk[q][3] = k3; }
+                else {
+                    if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
+                    if (q == 1) sts_int4<kRowInts * 4>(sa, k0, k1, k2, k3);
+                    if (q == 2) sts_int4<2 * kRowInts * 4>(sa, k0, k1, k2, k3);
+                    if (q == 3) sts_int4<3 * kRowInts * 4>(sa, k0, k1, k2, k3);
+                }
             } else {
                 // score only: remember the first column of this row that reaches its maximum
                 // (strict '>' keeps the earliest column, i.e. the earliest anti-diagonal of the row);
@@ -640,29 +597,38 @@ struct Strip {
             }
             u0 = h0; u1 = h1; u2 = h2; u3 = h3;          // the row above the next row
         }
+        if (STORE && SWB_STAGE_LATE) {
+#pragma unroll
+            for (int q = 0; q < kR; ++q) {
+                if (q == 0) sts_int4<0>(sa, kk[q][0], kk[q][1], kk[q][2], kk[q][3]);
+                if (q == 1) sts_int4<kRowInts * 4>(sa, kk[q][0], kk[q][1], kk[q][2], kk[q][3]);
+                if (q == 2) sts_int4<2 * kRowInts * 4>(sa, kk[q][0], kk[q][1], kk[q][2], kk[q][3]);
+                if (q == 3) sts_int4<3 * kRowInts * 4>(sa, kk[q][0], kk[q][1], kk[q][2], kk[q][3]);
+            }
+        }
         if (STORE) sa = ((sa + 16u) & (unsigned)(KT * 16 - 1)) | sa_base;
 
         // ---------------- hand my last row to the next strip (lane 31 only) ----------------
         {
             const int started = 1;   // (blocks j < 0 go out as well: wrong-epoch ring entries / the spare blocks of the boundary row)
             (void)j;
-            const int4 o = make_int4(u0 | (LAST ? otag_w : otag), u1, u2, u3);
+            // (PROF: u0 ends in kH7 = 0111b and otag / otag_w arrive as tag ^ 7: one XOR leaves the tag in the low bits)
+            const int4 o = make_int4(PROF ? (u0 ^ (LAST ? otag_w : otag)) : (u0 | (LAST ? otag_w : otag)), u1, u2, u3);
             if (LAST) sts_volatile_int4_if<0>(out_w, o, out_ring & started);
             else      sts_volatile_int4_if<16 * I>(out_g, o, out_ring & started);
             st_cg_int4_if<16 * I>(gout, o, out_glob & started);
         }
         // ---------------- scores of the next step ----------------
-        if constexpr (!PROF) {
-            if (MODE & 1) head_fix(next_word, j + 1);
-            else          scores(next_word);
-        }
+        if constexpr (PROF) lookup(next_word);
+        else if (MODE & 1)  head_fix(next_word, j + 1);
+        else                scores(next_word);
 
         // ---------------- the row above, for the next step ----------------
         // (v is valid by construction: compute_strip waited for the last block of this run of steps.  A tag
         // check with a spin loop HERE costs ~80 clk per step even when it never spins: the branch cuts the
         // group into basic blocks and ptxas can no longer overlap the tail of one step with the head of the next.)
         const bool l0 = (lane == 0);
-        A0 = l0 ? (v.x & ~15) : n0;
+        A0 = l0 ? (PROF ? ((v.x & ~15) | h7r) : (v.x & ~15)) : n0;
         A1 = l0 ? v.y : n1;
         A2 = l0 ? v.z : n2;
         A3 = l0 ? v.w : n3;
@@ -677,52 +643,29 @@ template <int KT, bool STORE, bool PROF>
 __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STORE, PROF>& S, const unsigned* aw,
                                               const unsigned staged, const unsigned drained,
                                               const unsigned consumed_in, const unsigned consumed_out,
-                                              const bool ring_consumer, const long long strip,
-                                              const unsigned progress, const unsigned fed)
+                                              const bool ring_consumer, const long long strip)
 {
     const int lane = S.lane;
     trace_stamp(p, strip, 0, lane);
     unsigned cur[kGroup + 1], nxt[kGroup];
-    int known_fed = -(1 << 30);
-    if constexpr (PROF) {
 #pragma unroll
-        for (int i = 0; i < kGroup + 1; ++i) cur[i] = 0;
-#if SWB_PROF_SMEM
-        // the feeder warp publishes the number of profile blocks it has staged (blocks < fed are in the ring)
-        do { known_fed = lds_volatile_int(fed); } while (known_fed < kGroup + prof_depth(KT, STORE));
-#pragma unroll
-        for (int q = 0; q < kR; ++q) {
-            S.rg[q] = S.rb[q] + 16u * (unsigned)((0 - lane) & (kPRing - 1));
-#pragma unroll
-            for (int i = 0; i < prof_depth(KT, STORE); ++i) S.pf[q][i] = lds_volatile_int4<0>(S.rg[q] + 16u * (unsigned)i);
-        }
-#else
-#pragma unroll
-        for (int q = 0; q < kR; ++q)
-#pragma unroll
-            for (int i = 0; i < prof_depth(KT, STORE); ++i) S.pf[q][i] = Strip<KT, STORE, PROF>::ldg_prof(S.pg[q] + i);
-#endif
-    } else {
-#pragma unroll
-        for (int i = 0; i < kGroup; ++i) cur[i] = __ldg(aw + i);
-    }
+    for (int i = 0; i < kGroup; ++i) cur[i] = __ldg(aw + i);
 
     // first input block (block 0 -> ring index 32, epoch 0 -> tag 1); all lanes poll
     if (S.has_in) {
         int4 v = lds_volatile_int4<16 * 32>(S.ring_in);
         while ((v.x & 3) != 1) { if (SWB_X_GATESLEEP > 0) __nanosleep(SWB_X_GATESLEEP); v = lds_volatile_int4<16 * 32>(S.ring_in); }
-        if (lane == 0) { S.A0 = v.x & ~15; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w; }
+        if (lane == 0) { S.A0 = (v.x & ~15) | S.kH7; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w; }
     }
     trace_stamp(p, strip, 1, lane);
 #ifdef SWB_X_CLKTRACE
     const long long clk_gate = clock64();
 #endif
-    // (with the score profile a NUL byte in b needs no care: positions outside a never match whatever the letter)
+    // (with the score look-up a NUL byte in b needs no care: positions outside a carry the pad code, which matches no row)
     const bool forced = (STORE && p.left_in != nullptr) || (!PROF && opaque(*p.nul_flag) != 0);
-    if constexpr (!PROF) {
-        if (forced) S.head_fix(cur[0], -lane);
-        else        S.scores(cur[0]);
-    }
+    if constexpr (PROF) S.lookup(cur[0]);
+    else if (forced)    S.head_fix(cur[0], -lane);
+    else                S.scores(cur[0]);
 
     const int gtail = (p.jmax - 8) >> 3;          // groups g <= gtail: t+1 <= jmax for all their steps
     int known_drained = 0, known_consumed = 0;
@@ -756,42 +699,30 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         const long long gd1 = clock64();
 #endif
         // ---- hand-off ring space (blocks up to t0+7-31 are written in this group)
-        if (ring_consumer && t0 - 80 > known_consumed) {
+        if (ring_consumer && t0 - (kRing + 16) > known_consumed) {
             int c;
-            do { c = lds_volatile_int(consumed_out); } while (c < t0 - 80);
+            do { c = lds_volatile_int(consumed_out); } while (c < t0 - (kRing + 16));
             known_consumed = c;
         }
 #ifdef SWB_X_GROUPTRACE
         if (g >= SWB_X_GT_LO && g < SWB_X_GT_HI) { const long long gd2 = clock64(); dbg_drain += gd1 - gd0; dbg_cons += gd2 - gd1; }
 #endif
         sts_volatile_int_if(consumed_in, t0, S.has_in & (lane == 0 ? 1 : 0));
-#if SWB_PROF_SMEM
-        if constexpr (PROF) {
-            // profile ring: this group's loads reach block t0 + kGroup - 1 + depth (lane 0); tell the feeder where I am
-            const int need = t0 + kGroup + prof_depth(KT, STORE);
-            if (need > known_fed) { do { known_fed = lds_volatile_int(fed); } while (known_fed < need); }
-            sts_volatile_int_if(progress, t0, lane == 0 ? 1 : 0);
-#pragma unroll
-            for (int q = 0; q < kR; ++q) S.rg[q] = S.rb[q] + 16u * (unsigned)((t0 - lane) & (kPRing - 1));
-        }
-#endif
         // ---- sequence words of the next group
-        if constexpr (!PROF) {
 #pragma unroll
-            for (int i = 0; i < kGroup; ++i) nxt[i] = __ldg(aw + t0 + kGroup + i);
-            cur[kGroup] = nxt[0];
-        }
+        for (int i = 0; i < kGroup; ++i) nxt[i] = __ldg(aw + t0 + kGroup + i);
+        cur[kGroup] = nxt[0];
 
         // consumer side: block t -> ring index (t+32)&63, epoch ((t+32)>>6)&1
         const unsigned in_g  = S.ring_in + 16u * (unsigned)((t0 + 32) & (kRing - 1));
         const unsigned in_w  = S.ring_in + 16u * (unsigned)((t0 + 40) & (kRing - 1));
-        const int   want     = 1 + (((t0 + 32) >> 6) & 1);
-        const int   want_w   = 1 + (((t0 + 40) >> 6) & 1);
+        const int   want     = 1 + (((t0 + 32) >> kRingLog) & 1);
+        const int   want_w   = 1 + (((t0 + 40) >> kRingLog) & 1);
         // producer side: block t-31 -> ring index (t+1)&63, epoch ((t+1)>>6)&1 (= its (j+32) form)
         const unsigned out_g = S.ring_out + 16u * (unsigned)((t0 & (kRing - 1)) + 1);
         const unsigned out_w = S.ring_out + 16u * (unsigned)((t0 + 8) & (kRing - 1));
-        const int   otag     = 1 + ((t0 >> 6) & 1);
-        const int   otag_w   = 1 + (((t0 + 8) >> 6) & 1);
+        const int   otag     = (1 + ((t0 >> kRingLog) & 1)) ^ S.kH7;
+        const int   otag_w   = (1 + (((t0 + 8) >> kRingLog) & 1)) ^ S.kH7;
 
 #ifdef SWB_X_GROUPTRACE
         const long long gc1 = clock64();
@@ -836,15 +767,8 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         const long long gc2 = clock64();
 #endif
         S.gout += kGroup;
-        if constexpr (PROF) {
-#if !SWB_PROF_SMEM
 #pragma unroll
-            for (int q = 0; q < kR; ++q) S.pg[q] += kGroup;
-#endif
-        } else {
-#pragma unroll
-            for (int i = 0; i < kGroup; ++i) cur[i] = nxt[i];
-        }
+        for (int i = 0; i < kGroup; ++i) cur[i] = nxt[i];
         // ---- publish the staged group to the writers
         __syncwarp();
         if (STORE) sts_volatile_int_if(staged, g + 1, lane == 0 ? 1 : 0);
@@ -1108,7 +1032,7 @@ __device__ __forceinline__ void loader_band(const int4* src, const int nblocks, 
         int4 v = make_int4(0, 0, 0, 0);
         if (j < limit) {
             v = ld_cg_int4(src + j);
-            ok = (v.x & 3) == 1 + (((j + 32) >> 6) & 1);
+            ok = (v.x & 3) == 1 + (((j + 32) >> kRingLog) & 1);
         }
         const unsigned mask = __ballot_sync(0xffffffffu, ok);
         const int lead = (mask == 0xffffffffu) ? 32 : (__ffs(~mask) - 1);
@@ -1121,49 +1045,16 @@ __device__ __forceinline__ void loader_band(const int4* src, const int nblocks, 
     }
 }
 
-// ---------------------------------------------------------------------------------
-// feeder warp (SWB_PROF_SMEM): keeps the window of the score profile that the band's strips
-// are working on in the shared-memory ring -- blocks [lagging strip's t0 - 32, ... + kPRing) of the
-// letter rows in use -- and publishes the number of blocks staged
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ void feeder_band(const FillParams& p, int4* ring, const int lane, const int wpc,
-                                            volatile int* progress, volatile int* fed_flag, const int end)
-{
-    const int nl = *p.nletters;
-    const int nrows = nl + 1;                       // the letters of b and the row that never matches
-    int fed = -kProfPad;                            // next block to stage (blocks -31..-1: lanes that have not started)
-    while (fed < end) {
-        int lo = 0x7fffffff;
-        for (int w = 0; w < wpc; ++w) lo = min(lo, progress[w]);
-        if (lo == 0x7fffffff) break;                // every strip of the band has finished
-        const int hi = min(end, lo - 32 + kPRing);  // slots of blocks < lo - 32 are free: lane 31 of the slowest strip is at lo - 31
-        if (fed >= hi) { __nanosleep(400); continue; }
-        const int nb = hi - fed;
-        for (int it = lane; it < nb * nrows; it += 32) {
-            const int r = it / nb, j = fed + (it - r * nb);
-            const int row = (r == nl) ? kMaxLetters : r;
-            const int4 v = __ldg(p.prof + (long long)row * p.prof_stride + kProfPad + j);
-            const int slot = j & (kPRing - 1);
-            sts_volatile_int4(ring + row * kPRowInt4 + slot, v);
-            if (slot < kPMirror) sts_volatile_int4(ring + row * kPRowInt4 + kPRing + slot, v);
-        }
-        __syncwarp();
-        fed = hi;
-        if (lane == 0) *fed_flag = fed;
-    }
-}
-
 // threads per block for wpc strips per band: rows of 4 warps; the 4-wpc serving schedulers
-// hold wpc*kWriters writers (none in score-only mode) + the loader + the profile feeder
+// hold wpc*kWriters writers (none in score-only mode) + 1 loader
 __host__ __device__ constexpr int fill_block_threads(int wpc, bool store)
 {
-    return 32 * 4 * (((store ? wpc * kWriters : 0) + 1 + SWB_PROF_SMEM + (4 - wpc) - 1) / (4 - wpc));
+    return 32 * 4 * (((store ? wpc * kWriters : 0) + 1 + (4 - wpc) - 1) / (4 - wpc));
 }
 __host__ __device__ constexpr size_t fill_smem_bytes(int wpc, int KT, bool store)
 {
     return (size_t)wpc * ((store ? (size_t)kStripRows * 4 * KT * sizeof(int) + kWriters * 48 * sizeof(int4) : 0) +
-                          kRing * sizeof(int4)) +
-           (SWB_PROF_SMEM ? (size_t)kProfRows * kPRowInt4 * sizeof(int4) : 0);
+                          kRing * sizeof(int4));
 }
 
 // ---------------------------------------------------------------------------------
@@ -1176,16 +1067,16 @@ template <int KT, bool STORE, bool PROF>
 __global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true), (KT == 64 && STORE) ? 1 : 2)
 fill_kernel(const FillParams p_in)
 {
-    // both instantiations are launched; the alphabet of b (counted on the device by profile_kernel) decides which runs
+    // Both instantiations are launched; the alphabet of b (counted on the device by selector_kernel, so that the call
+    // stays asynchronous for device-resident sequences) decides which one runs.
 #ifdef SWB_X_FORCE_COMPARE                                     // developer build: always the character-compare instantiation
     if (PROF) return;
 #else
-    if ((*p_in.nletters <= kMaxLetters) != PROF) return;
+    if ((p_in.prof_ok != 0 && *p_in.nletters <= kMaxLetters) != PROF) return;
 #endif
     extern __shared__ __align__(1024) int4 smem4[];
     __shared__ int s_band;
     __shared__ int s_staged[kMaxWpc], s_drained[kMaxWpc * kWriters], s_consumed[kMaxWpc + 1];
-    __shared__ int s_progress[kMaxWpc], s_fed;     // profile ring: first step of each strip's current group / blocks staged
 
     const int lane = threadIdx.x & 31;
     const int wid  = threadIdx.x >> 5;
@@ -1200,7 +1091,6 @@ fill_kernel(const FillParams p_in)
     if (threadIdx.x < kMaxWpc) s_staged[threadIdx.x] = 0;
     if (threadIdx.x < kMaxWpc * kWriters) s_drained[threadIdx.x] = 0;
     if (threadIdx.x <= kMaxWpc) s_consumed[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_fed = -(1 << 30);
     __syncthreads();
     const int sched = ((wid & 3) + 4 - ((s_band * wpc) & 3)) & 3, wrow = wid >> 2;
     const int nserv = 4 - wpc;                                   // schedulers that serve writers / loader
@@ -1212,22 +1102,20 @@ fill_kernel(const FillParams p_in)
         const int slot = wrow * nserv + (sched - wpc);
         if (slot < nwriters) { role = 1; w = slot; }
         else if (slot == nwriters) role = 2;
-        else if (slot == nwriters + 1 && PROF && SWB_PROF_SMEM) role = 3;
     }
 
     int4* stage4  = smem4;                                       // [wpc][kStripRows][KT]   (STORE only)
     int4* rings   = stage4 + (STORE ? (size_t)wpc * kStripRows * KT : 0);   // [wpc][kRing]
     int4* rowtabs = rings + (size_t)wpc * kRing;                 // [wpc*kWriters][48]      (STORE only)
-    int4* pring   = rowtabs + (STORE ? (size_t)wpc * kWriters * 48 : 0);   // [kProfRows][kPRowInt4]  (SWB_PROF_SMEM)
 
-    for (int i = threadIdx.x; i < wpc * kRing; i += blockDim.x) rings[i] = make_int4(0, 0, 0, 0);
+    // (tag 0 = not valid yet; the first strip of a pair reads its never-written ring as the zero row above row 1)
+    for (int i = threadIdx.x; i < wpc * kRing; i += blockDim.x) rings[i] = make_int4(0, PROF ? kTieDiag : 0, PROF ? kTieDiag : 0, PROF ? kTieDiag : 0);
     __syncthreads();
     // tickets are handed out pair by pair, band by band: a waiting band's predecessor is resident
     const long long pair = s_band / p_in.nbands;
     const int band = s_band % p_in.nbands;
     FillParams p = p_in;
     p.a4 += pair * p.a4_stride;
-    p.prof += pair * p.prof_pair_stride;
     p.b += pair * p.n;
     p.H += pair * p.pair_stride; p.P += pair * p.pair_stride;
     p.boundary += pair * (long long)(p.nbands - 1) * p.bstride;
@@ -1235,34 +1123,42 @@ fill_kernel(const FillParams p_in)
     p.gmax += pair;
     if (!STORE) p.row_best += pair * (p.n + 1);
     const long long band_r0 = 1 + (long long)band * wpc * kStripRows;
-    if (threadIdx.x < kMaxWpc)
-        s_progress[threadIdx.x] = (threadIdx.x < wpc && band_r0 + (long long)kStripRows * threadIdx.x <= p.n) ? 0 : 0x7fffffff;
-    __syncthreads();
 
     if (role == 0) {
         // ------------------------------------------------ compute
         const long long r0 = band_r0 + (long long)kStripRows * w;
         if (r0 > p.n) return;
         Strip<KT, STORE, PROF> S;
+        constexpr int kH7 = Strip<KT, STORE, PROF>::kH7;
         S.lane = lane;
 #pragma unroll
         for (int q = 0; q < kR; ++q) {
             const long long row = r0 + kR * lane + q;
             S.b4[q] = (row <= p.n) ? (unsigned)p.b[row - 1] * 0x01010101u : 0u;
             S.inv[q] = (row <= p.n) ? 0u : 0x01010101u;
-            S.hl[q] = 0; S.rmax[q] = 0; S.rcol[q] = 0; S.kmax = 0;
+            S.hl[q] = kH7; S.rmax[q] = 0; S.rcol[q] = 0; S.kmax = 0;
             if constexpr (PROF) {
-                const int li = (row <= p.n) ? (int)p.lmap[p.b[row - 1]] : kMaxLetters;
-                S.pg[q] = p.prof + (long long)li * p.prof_stride + kProfPad - lane;      // block -lane of step 0
-                S.rb[q] = (unsigned)__cvta_generic_to_shared(pring + (size_t)li * kPRowInt4);
+                // score bytes of this row's character against the codes 0..7: match for its own code, mismatch for the
+                // others (the pad code and rows past n never match)
+                const unsigned mm = (unsigned)p.mismatch8 & 0xffu, mt = (unsigned)p.match8 & 0xffu;
+                const unsigned code = (row <= p.n) ? (unsigned)p.lmap[p.b[row - 1]] : (unsigned)kPadCode;
+                unsigned lo = mm * 0x01010101u, hi = mm * 0x01010101u;
+                if (code < 4) lo = (lo & ~(0xffu << (8 * code))) | (mt << (8 * code));
+                else if (code < kPadCode) hi = (hi & ~(0xffu << (8 * (code - 4)))) | (mt << (8 * (code - 4)));
+                S.tlo[q] = lo; S.thi[q] = hi;
+            } else {
+                S.tlo[q] = S.thi[q] = 0u;
             }
+            S.sb[q] = 0;
         }
         S.one = opaque(1);
+        S.h7r = opaque(kH7);
         // keep the scoring constants in registers: a shuffle result is opaque to ptxas, which
         // otherwise re-reads them from the constant bank at the head of every step, on the
         // dependency chain
-        S.sm = opaque(p.s_match); S.sx = opaque(p.s_mismatch); S.gu = opaque(p.g_up); S.gl = opaque(p.g_left); S.g16 = opaque(p.g_left - kTieLeft);
-        S.A0 = S.A1 = S.A2 = S.A3 = 0; S.dgp = 0;
+        // (PROF: the H operands carry kH7 in their low bits, the gap constants take it off again)
+        S.sm = opaque(p.s_match); S.sx = opaque(p.s_mismatch); S.gu = opaque(p.g_up - kH7); S.gl = opaque(p.g_left - kH7); S.g16 = opaque(p.g_left - kTieLeft);
+        S.A0 = S.A1 = S.A2 = S.A3 = kH7; S.dgp = kH7;
         S.sa_base = (unsigned)__cvta_generic_to_shared(stage4 + ((size_t)w * kStripRows + (size_t)kR * lane) * KT);
         S.sa = S.sa_base + 16u * (unsigned)lane;                 // slot (t + lane) & (KT-1) at t = 0
         S.ring_in  = (unsigned)__cvta_generic_to_shared(rings + (size_t)w * kRing);
@@ -1295,11 +1191,11 @@ fill_kernel(const FillParams p_in)
                     const long long row = r0 + kR * lane + q;
                     int hv = 0;
                     if (row <= p.n) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(hv) : "l"(p.left_in + row) : "memory");
-                    S.lb[q] = 16 * hv - g16;
+                    S.lb[q] = 16 * hv - g16 + kH7;
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < kR; ++q) S.lb[q] = -g16;
+                for (int q = 0; q < kR; ++q) S.lb[q] = -g16 + kH7;
             }
         }
         S.has_in = opaque(r0 > 1 ? 1 : 0);
@@ -1315,9 +1211,7 @@ fill_kernel(const FillParams p_in)
         compute_strip<KT, STORE, PROF>(p, S, aw, (unsigned)__cvta_generic_to_shared(s_staged + w),
                       (unsigned)__cvta_generic_to_shared(s_drained + w * kWriters),
                       (unsigned)__cvta_generic_to_shared(s_consumed + w),
-                      (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, strip + pair * p.nstrips,
-                      (unsigned)__cvta_generic_to_shared(s_progress + w), (unsigned)__cvta_generic_to_shared(&s_fed));
-        if (PROF && SWB_PROF_SMEM && lane == 0) *(volatile int*)(s_progress + w) = 0x7fffffff;    // the feeder may stop minding me
+                      (unsigned)__cvta_generic_to_shared(s_consumed + w + 1), ring_consumer, strip + pair * p.nstrips);
         if (STORE && SWB_KMAXC) {
             // strip maximum (omp_smithW.c:384-387 needs only the arg-max; see argmax_kernel).  The rows past n of a
             // partial strip never match (inv), so their cells stay below the cells above them.
@@ -1350,10 +1244,6 @@ fill_kernel(const FillParams p_in)
         // ------------------------------------------------ loader
         if (band == 0 || band_r0 > p.n) return;
         loader_band(p.boundary + (size_t)(band - 1) * p.bstride + kBoundaryPad, p.jmax + 1, rings, lane, s_consumed);
-    } else if (role == 3) {
-        // ------------------------------------------------ profile feeder
-        if (band_r0 > p.n) return;
-        feeder_band(p, pring, lane, wpc, s_progress, &s_fed, p.ngroups * kGroup + 16);
     }
 }
 
@@ -1461,6 +1351,7 @@ __global__ void finalize_kernel(const unsigned long long* key, const int* gmax, 
     if (maxScore) maxScore[pair] = g;
 }
 
+#ifndef SWB_FILL_ONLY
 // ---------------------------------------------------------------------------------
 // backtrack (omp_smithW.c:405-420): follow P from maxPos until a NONE cell, negating
 // the path in place.  The chain is serial, so the kernel hides the HBM latency and keeps
@@ -1691,4 +1582,6 @@ backtrack_kernel(int32_t* P, long long pitch, long long maxPos_arg,
 #endif
 }
 
-}  // namespace swb
+#endif  // SWB_FILL_ONLY
+
+}  // namespace SWB_NS

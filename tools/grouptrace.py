@@ -4,7 +4,7 @@ swb = importlib.import_module("smith-waterman_b200")
 import os
 cols=rows=int(os.environ.get("SHAPE","8192"))
 wpc=int(sys.argv[1]) if len(sys.argv)>1 else 2
-SR=int(sys.argv[2]) if len(sys.argv)>2 else 64
+SR=int(sys.argv[2]) if len(sys.argv)>2 else 96
 dev=torch.device("cuda:0")
 a,b=swb.generate(42,cols,rows)
 a_d=torch.frombuffer(bytearray(a),dtype=torch.uint8).to(dev); b_d=torch.frombuffer(bytearray(b),dtype=torch.uint8).to(dev)

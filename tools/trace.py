@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 a, b = swb.generate(42, cols, rows)
 a_d = torch.frombuffer(bytearray(a), dtype=torch.uint8).to(dev); b_d = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
 dH = torch.empty((rows + 1) * (cols + 1), dtype=torch.int32, device=dev); dP = torch.empty_like(dH)
-strips = (rows + 63) // 64
+strips = (rows + 95) // 96          # single pairs run the 96-row geometry (three rows per lane)
 for it in range(2):
     tr = torch.zeros(strips * 8, dtype=torch.int64, device=dev)
     swb.fill_async(a_d, cols, b_d, rows, dH, dP, cols + 1, None, None, warps_per_band=args.wpc, trace=tr)
