@@ -179,6 +179,8 @@ def time_reference_cpu(side_cols: int, side_rows: int, all_thread_probe: bool = 
         best = dict(sec=time.perf_counter() - t0, cores=1, cols=side_cols, rows=side_rows)
         notes.append("oracle/_ref missing: timed the C restatement (wavefront order) instead")
     gcups = best["cols"] * best["rows"] / best["sec"] / 1e9
+    if swo.REF_BIN.exists():
+        extra["one_thread_seconds"] = t1_fill + (t1_bt or 0.0)
     out = {"value": gcups, "unit": UNIT, "cores": best["cores"], "kind": kind, "host_cpus": ncpu,
            "sample": f"{best['cols']}x{best['rows']} of the workload, seed {SEED}; " + "; ".join(notes),
            "seconds": best["sec"], "cells": best["cols"] * best["rows"]}
@@ -229,10 +231,18 @@ def run_reference_arm(args):
     for k in range(max(0, args.steps - (1 if full else 0))):
         r = time_reference_cpu(min(full_c, sample), min(full_r, sample), all_thread_probe=(full is None and k == 0))
         checks.append(r)
-    if full is not None:
-        # (time_reference_cpu keeps the faster of 1 thread on the full pass and all threads on a 1024^2 probe)
+    if full is not None and "one_thread_seconds" in full:
+        # The basis is the FULL pass on one thread.  The all-thread configuration is only probed at 1024^2, where every
+        # anti-diagonal is shorter than CUTOFF = 1024 and the `omp parallel for if(nEle >= CUTOFF)` never forks
+        # (omp_smithW.c:209): its rate there is a cache-resident serial rate, not a multi-thread one, and at full size the
+        # per-cell `omp critical` (:384-387) makes threads a slowdown (6-12x).  It is reported, not used.
+        basis = dict(full)
+        basis.update(value=full_c * full_r / full["one_thread_seconds"] / 1e9, cores=1, seconds=full["one_thread_seconds"],
+                     cells=full_c * full_r)
+        what = f"one full {full_c}x{full_r} pass, 1 thread"
+    elif full is not None:
         basis = full
-        what = f"one full {full_c}x{full_r} pass" if basis["cells"] == full_c * full_r else basis["sample"]
+        what = basis["sample"]
     else:
         basis = max(checks, key=lambda r: r["value"])
         what = f"{sample}x{sample} prefix (no full pass: --ref-full 0 or not enough host memory)"
@@ -257,7 +267,7 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------- helpers of our arm
-KERNELS_PER_FILL = ["prep_kernel", "profile_kernel", "fill_kernel<PROF>", "fill_kernel<no PROF> (returns at once)",
+KERNELS_PER_FILL = ["prep_kernel", "selector_kernel", "fill_kernel<look-up>", "fill_kernel<compare> (returns at once)",
                     "argmax_kernel", "finalize_kernel"]
 
 
@@ -492,7 +502,7 @@ def run_single(args, torch, swb, dev, local):
         except (ValueError, OSError):
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_source, "kernel": "swb::fill_kernel<64,true,true>",
+                "traffic": traffic, "traffic_source": traffic_source, "kernel": "swb_tall::fill_kernel<64,true,true> (96-row strips, score look-up)",
                 "kernel_ms_avg": fill_avg, "kernel_ms_min": min(fill_ms), "algorithmic_bytes_per_launch": 8 * cells_padded,
                 "peak_source": peak_src, "fill_gcups": cols * rows / (fill_avg * 1e-3) / 1e9}
 
@@ -583,6 +593,7 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
         result["maxPos"] = mp
         result["path_len"] = pipe.backtrack(mp)            # right-to-left hops over the strips, one broadcast each
 
+    # ---- (1) one step at a time: fill on every rank, maxPos all-gather, backtrack hops (the latency of a step)
     for _ in range(args.warmup):
         step()
     barrier()
@@ -595,9 +606,79 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
     e1.record(stream)
     barrier()
     t_host = time.perf_counter() - t_host0
-    total_ms = e0.elapsed_time(e1)
+    serial_total_ms = e0.elapsed_time(e1)
+    total_ms = serial_total_ms
     fill_ms = [t.elapsed_ms() for t in timers]
     maxPos, plen = result["maxPos"], result["path_len"]
+
+    # ---- (2) the same K steps as a pipeline over two sets of strip buffers (as at N = 1): the maxPos all-gather and the
+    # backtrack hops of step k run on a second stream while the fill kernels of step k+1 are already running; every step
+    # still does all of its work and the timed region ends when the last backtrack has finished.
+    pipelined = not args.no_pipeline
+    pipe2 = None
+    if pipelined:
+        try:
+            pipe2 = strips.StripPipeline(a, b, local)
+        except Exception:                                   # not enough device memory for a second buffer set
+            pipelined = False
+    ok_t = torch.tensor([1 if pipelined else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    pipelined = bool(ok_t.item())
+    if pipelined:
+        pipes = [pipe, pipe2]
+        s_fill = torch.cuda.Stream(device=dev)
+        s_bt = torch.cuda.Stream(device=dev, priority=-1)
+        ptimers = [swb.KernelTimer(local) for _ in range(args.steps)]
+        presult = {}
+
+        def finish(pp, ev):
+            with torch.cuda.stream(s_bt):
+                s_bt.wait_event(ev)
+                mp = pp.maxpos()
+                presult["maxPos"] = mp
+                presult["path_len"] = pp.backtrack(mp, stream=s_bt)
+
+        def run_pipeline(nsteps, use_timers):
+            evs = [torch.cuda.Event() for _ in range(nsteps)]
+            for k in range(nsteps):
+                pipes[k % 2].fill_async(stream=s_fill, timer=ptimers[k] if use_timers else None)
+                evs[k].record(s_fill)
+                if k >= 1:
+                    finish(pipes[(k - 1) % 2], evs[k - 1])
+            finish(pipes[(nsteps - 1) % 2], evs[nsteps - 1])
+
+        run_pipeline(max(args.warmup, 2), False)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        p0.record(s_fill)
+        run_pipeline(args.steps, True)
+        p1.record(s_bt)
+        barrier()
+        total_ms = p0.elapsed_time(p1)
+        fill_ms = [t.elapsed_ms() for t in ptimers]
+        assert (presult["maxPos"], presult["path_len"]) == (maxPos, plen), "pipelined steps disagree with the serial ones"
+        # leave `pipe` holding the result of a complete step (fill + backtrack) for the parity checks below
+        step()
+        pipe2.close(); pipe2 = None
+        torch.cuda.empty_cache()
+
+    # the path digest is checked after the last timed backtrack: gather the negated cells of every strip
+    neg_local = []
+    Pv = st.dP.view(rows + 1, st.pitch)
+    for r0 in range(0, rows + 1, 8192):
+        idx = torch.nonzero(Pv[r0:r0 + 8192, 1:] < 0)
+        if idx.numel():
+            neg_local.append((idx[:, 0] + r0) * (cols + 1) + idx[:, 1] + 1 + st.col0)
+    neg_local = torch.cat(neg_local) if neg_local else torch.zeros(0, dtype=torch.int64, device=dev)
+    cnt = torch.tensor([neg_local.numel()], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    mx = max(int(c.item()) for c in cnts)
+    padded = torch.full((max(mx, 1),), -1, dtype=torch.int64, device=dev)
+    padded[:neg_local.numel()] = neg_local
+    allneg = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(allneg, padded)
 
     # fill only (no maxPos gather, no backtrack), barrier before each: the kernel-level picture per rank
     fo = []
@@ -616,24 +697,7 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
     if g is not None:
         Hv = st.dH.view(rows + 1, st.pitch); Pv = st.dP.view(rows + 1, st.pitch)
         checked, bad = check_digests(g, Hv, Pv, st.col0, st.m)
-    # the path digest is checked after the last timed backtrack: gather the negated cells of every strip
-    neg_local = []
-    Pv = st.dP.view(rows + 1, st.pitch)
-    for r0 in range(0, rows + 1, 8192):
-        idx = torch.nonzero(Pv[r0:r0 + 8192, 1:] < 0)
-        if idx.numel():
-            neg_local.append((idx[:, 0] + r0) * (cols + 1) + idx[:, 1] + 1 + st.col0)
-    neg_local = torch.cat(neg_local) if neg_local else torch.zeros(0, dtype=torch.int64, device=dev)
-    cnt = torch.tensor([neg_local.numel()], dtype=torch.int64, device=dev)
-    cnts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(cnts, cnt)
-    mx = max(int(c.item()) for c in cnts)
-    padded = torch.full((max(mx, 1),), -1, dtype=torch.int64, device=dev)
-    padded[:neg_local.numel()] = neg_local
-    allneg = [torch.zeros_like(padded) for _ in range(world)]
-    dist.all_gather(allneg, padded)
-
-    t = torch.tensor([total_ms, min(fo), statistics.mean(fill_ms), float(checked), float(bad)], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, min(fo), statistics.mean(fill_ms), float(checked), float(bad), serial_total_ms], dtype=torch.float64, device=dev)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
     kt = torch.tensor([statistics.mean(fill_ms)], dtype=torch.float64, device=dev)
@@ -754,7 +818,13 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
                            "parallelism": f"{world} column strips, one process per GPU; boundary column pushed to the right neighbour with "
                                           "st.relaxed.sys over NVLink inside the fill kernel, per-32-row release flags; NCCL carries only the "
                                           "maxPos all-gather (3 int64 per rank) and one 3-word broadcast per backtrack hop",
-                           "timing": "CUDA events on each rank's stream around the K steps, max over ranks; barrier + synchronize on both sides"},
+                           "timing": "CUDA events on each rank's streams around the K steps, max over ranks; barrier + synchronize on both sides",
+                           "pipeline": ("two sets of strip buffers per GPU: the maxPos all-gather and the backtrack hops of step k run beside "
+                                        "the fill kernels of step k+1; every step does all of its work inside the timed region"
+                                        if pipelined else "none: fill, maxPos, backtrack back to back")},
+                "serial": {"ms_per_step": float(tmax[5].item()) / args.steps,
+                           "value": cols * rows / (float(tmax[5].item()) / args.steps * 1e-3) / 1e9,
+                           "what": "the same K steps one at a time (latency of a step: fill on all ranks, maxPos all-gather, backtrack hops)"},
                 "fill_only": {"ms_max_over_ranks": float(tmax[1].item()), "gcups": cols * rows / float(tmax[1].item()) / 1e6,
                               "what": "the strips' fill kernels alone (prep + fill + argmax per rank), barrier before each, best of 3"},
                 "kernel_ms_per_rank": [round(x, 3) for x in kernel_ms],
@@ -762,7 +832,7 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": nk * args.steps * world,
                 "kernels_per_step": KERNELS_PER_FILL + ["backtrack_kernel (on the ranks the path crosses)"],
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
-                             "traffic": None, "traffic_source": None, "kernel": "swb::fill_kernel<64,true,true> (column-strip mode), all ranks",
+                             "traffic": None, "traffic_source": None, "kernel": "swb_tall::fill_kernel<64,true,true> (column-strip mode), all ranks",
                              "kernel_ms_avg": max(kernel_ms), "algorithmic_bytes_per_launch": 8 * cells_padded,
                              "peak_source": peak_src + f" x {world} GPUs",
                              "what": "bytes of all strips / slowest rank's fill kernel time / (N x measured HBM peak)"},

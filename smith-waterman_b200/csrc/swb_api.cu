@@ -19,8 +19,8 @@
 #include <mutex>
 
 #ifndef SWB_BT2
-#define SWB_BT2 0                      // 1: the jump-table backtrack kernel (swb_backtrack.cuh); 0: the single-walker kernel
-#endif
+#define SWB_BT2 0                      // 1: every backtrack runs the jump-table kernel (swb_backtrack.cuh); 0: only the ones
+#endif                                 //    that emit moves do (measured equal: 2.0 ms for 53 856 cells)
 
 namespace {
 
@@ -377,19 +377,19 @@ int launch_backtrack(int32_t* dP, int64_t pitch, int64_t maxPos, const int64_t* 
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#if SWB_BT2
-    SWB_CUDA(cudaFuncSetAttribute(swb::bt2::backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, swb::bt2::kSmemBytes));
-    swb::bt2::backtrack_kernel<<<1, swb::bt2::kThreads, swb::bt2::kSmemBytes, st>>>(
-        dP, pitch, maxPos, reinterpret_cast<const long long*>(d_maxPos), reinterpret_cast<long long*>(d_pathLen),
-        reinterpret_cast<long long*>(d_endPos), d_moves);
-#else
-    if (d_moves) return SWB_ERR_ARG;                                      // (the single-walker kernel does not emit moves)
+    if (SWB_BT2 || d_moves) {
+        SWB_CUDA(cudaFuncSetAttribute(swb::bt2::backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, swb::bt2::kSmemBytes));
+        swb::bt2::backtrack_kernel<<<1, swb::bt2::kThreads, swb::bt2::kSmemBytes, st>>>(
+            dP, pitch, maxPos, reinterpret_cast<const long long*>(d_maxPos), reinterpret_cast<long long*>(d_pathLen),
+            reinterpret_cast<long long*>(d_endPos), d_moves);
+        SWB_CUDA(cudaGetLastError());
+        return SWB_OK;
+    }
     const int bt_smem = (2 * (swb::kBtPad + swb::kBtBandInts) + 2 * swb::kBtList) * (int)sizeof(int);
     SWB_CUDA(cudaFuncSetAttribute(swb::backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt_smem));
     swb::backtrack_kernel<<<1, swb::kBtThreads, bt_smem, st>>>(dP, pitch, maxPos, reinterpret_cast<const long long*>(d_maxPos),
                                                                reinterpret_cast<long long*>(d_pathLen),
                                                                reinterpret_cast<long long*>(d_endPos));
-#endif
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;
 }

@@ -325,8 +325,9 @@ class StripPipeline:
         self._unjoined_fills = 0
         return mp
 
-    def backtrack(self, maxPos: int) -> int:
-        return distributed_backtrack(self.parts, maxPos, self.m, self.rank, self.strip.walk, self.dist, self.tdev)
+    def backtrack(self, maxPos: int, stream=None) -> int:
+        return distributed_backtrack(self.parts, maxPos, self.m, self.rank,
+                                     lambda i, jl: self.strip.walk(i, jl, stream=stream), self.dist, self.tdev)
 
     def close(self):
         self.dist.barrier()

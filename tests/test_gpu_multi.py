@@ -121,3 +121,38 @@ def test_cli_files_manifest_devices(swb, oracle, tmp_path):
     a42, b42 = swb.generate(42, 700, 500)
     ms, mp = oracle.score_only(a42, b42)
     assert f"maxScore: {ms}  maxPos: {mp}" in out
+
+
+def test_traceback_moves_cigar(swb, oracle):
+    """the backtrack that also emits the path's moves (swb_traceback_async, the jump-table kernel)
+    against a host walk of the oracle's P (omp_smithW.c:405-420); CIGAR / gapped strings from the moves."""
+    for (m, n, seed) in [(8, 9, None), (700, 500, 3), (3000, 2600, 5), (257, 4000, 6)]:
+        if seed is None:
+            a, b = b"TGTTACGG", b"GGTTGACTA"
+        else:
+            a, b = make_pair(seed, m, n)
+        Ho, Po, mpo = oracle.fill(a, b, order="wavefront")
+        want, pos = bytearray(), mpo
+        while Po.reshape(-1)[pos] != 0:
+            code = int(Po.reshape(-1)[pos]); want.append(code)
+            pos -= {3: m + 2, 1: m + 1, 2: 1}[code]
+        dev = torch.device("cuda:0")
+        dH = torch.empty((n + 1) * (m + 1), dtype=torch.int32, device=dev); dP = torch.empty_like(dH)
+        d_pos = torch.zeros(1, dtype=torch.int64, device=dev)
+        swb.fill_async(a, m, b, n, dH, dP, m + 1, d_pos, None, stream=torch.cuda.current_stream())
+        d_len = torch.zeros(1, dtype=torch.int64, device=dev); d_end = torch.zeros(1, dtype=torch.int64, device=dev)
+        d_moves = torch.zeros(m + n + 2, dtype=torch.uint8, device=dev)
+        swb.traceback_async(dP, m + 1, d_startPos=d_pos, d_pathLen=d_len, d_endPos=d_end, d_moves=d_moves,
+                            stream=torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        plen = int(d_len.item())
+        assert int(d_pos.item()) == mpo and plen == len(want) and int(d_end.item()) == pos
+        moves = bytes(d_moves[:plen].cpu().numpy())
+        assert moves == bytes(want)
+        Pb = Po.copy(); oracle.backtrack(Pb, mpo)
+        assert (dP.view(n + 1, m + 1).cpu().numpy() == Pb).all()
+        ga, gb = swb.alignment_from_moves(moves, a, b, mpo, m + 1)
+        score = sum(-2 if (x == 45 or y == 45) else (3 if x == y else -3) for x, y in zip(ga, gb))
+        assert score == Ho.reshape(-1)[mpo]
+        if seed is None:
+            assert swb.cigar_from_moves(moves) == "3M1I2M"
