@@ -489,7 +489,9 @@ def run_single(args, torch, swb, dev, local):
 
     # ---- roofline of the dominant kernel (the fill): 8 B per cell, HBM-write bound
     peak, peak_src = hbm_peak()
-    fill_avg = statistics.mean(fill_ms)
+    # the kernel timed ALONE: its CUDA events in the one-at-a-time timed steps (in the pipelined region the backtrack
+    # kernel of the previous step holds one SM and some bandwidth beside it; that average is reported next to it)
+    fill_avg = statistics.mean(fill_ms_serial)
     achieved = 8.0 * cells_padded / (fill_avg * 1e-3) / 1e9
     traffic, traffic_source = None, None
     tf = ROOT / "profiles" / "fill_traffic.json"            # written from the ncu --set full capture
@@ -503,7 +505,9 @@ def run_single(args, torch, swb, dev, local):
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_source, "kernel": "swb_tall::fill_kernel<64,true,true> (96-row strips, score look-up)",
-                "kernel_ms_avg": fill_avg, "kernel_ms_min": min(fill_ms), "algorithmic_bytes_per_launch": 8 * cells_padded,
+                "kernel_ms_avg": fill_avg, "kernel_ms_min": min(fill_ms_serial), "kernel_ms_avg_in_pipelined_region": statistics.mean(fill_ms),
+                "timed_in": "the K one-at-a-time timed steps (`serial`), CUDA events around the launch on its stream",
+                "algorithmic_bytes_per_launch": 8 * cells_padded,
                 "peak_source": peak_src, "fill_gcups": cols * rows / (fill_avg * 1e-3) / 1e9}
 
     secondary = None
@@ -570,6 +574,27 @@ def run_single(args, torch, swb, dev, local):
     return 0
 
 
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Pins this rank to the CPUs closest to its GPU (NVML's CPU affinity of the device) so that the pinned host
+    buffers it allocates next are first-touched on that NUMA node: with 8 ranks copying 10 GB each to host memory
+    on arbitrary nodes the copies shared the inter-socket links (round 1: an N=8 e2e step took 4.5x an N=1 step)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + bit for w, word in enumerate(words) for bit in range(64) if (word >> bit) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} CPUs of GPU {local}'s NUMA node"
+        return "NVML affinity outside this container's CPU set: not bound"
+    except Exception as e:                                   # affinity is an optimisation, never a failure
+        return f"not bound ({type(e).__name__})"
+
+
 # --------------------------------------------------------------------------- our arm, N > 1: one pair in N column strips
 def run_strips(args, torch, dist, swb, dev, local, rank, world):
     strips = importlib.import_module("smith-waterman_b200.strips")
@@ -609,6 +634,7 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
     serial_total_ms = e0.elapsed_time(e1)
     total_ms = serial_total_ms
     fill_ms = [t.elapsed_ms() for t in timers]
+    fill_ms_serial = list(fill_ms)
     maxPos, plen = result["maxPos"], result["path_len"]
 
     # ---- (2) the same K steps as a pipeline over two sets of strip buffers (as at N = 1): the maxPos all-gather and the
@@ -700,7 +726,7 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
     t = torch.tensor([total_ms, min(fo), statistics.mean(fill_ms), float(checked), float(bad), serial_total_ms], dtype=torch.float64, device=dev)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    kt = torch.tensor([statistics.mean(fill_ms)], dtype=torch.float64, device=dev)
+    kt = torch.tensor([statistics.mean(fill_ms_serial)], dtype=torch.float64, device=dev)      # the kernels of the one-at-a-time steps
     allk = [torch.zeros_like(kt) for _ in range(world)]
     dist.all_gather(allk, kt)
     sampler = ClockSampler(local)
@@ -766,6 +792,7 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
     if not args.no_e2e:
         try:
             torch.cuda.empty_cache()
+            numa = bind_to_gpu_numa_node(local)
             pipe2 = strips.StripPipeline(a, b, local)
             s2 = pipe2.strip
             nloc = (rows + 1) * s2.pitch
@@ -794,6 +821,7 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
             dt = float(te.item())
             e2e = {"value": cols * rows / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": cols + rows * world,
                    "d2h_bytes_per_step": 8 * (rows + 1) * (cols + world) + 24 * world, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+                   "host_placement": numa,
                    "api": "StripPipeline (swb_fill_strip_async / swb_backtrack_from_async per rank): host a, b -> each rank's strip of "
                           "H and P (after backtrack) in pinned host memory, maxPos, path length"}
             pipe2.close()

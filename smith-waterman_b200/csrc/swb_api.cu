@@ -130,13 +130,13 @@ namespace {
 // The one implementation behind swb_fill_async, swb_fill_batch_async and swb_score_only_async.
 //   npairs equally shaped pairs: a = npairs*m bytes, b = npairs*n bytes, pair k's matrices at
 //   dH/dP + k*pair_stride; d_maxPos / d_maxScore hold npairs entries.  store == false: score only.
-// Single pairs with H/P stores run the three-rows-per-lane geometry (96-row strips: a third fewer links in the
-// strip-to-strip chain that bounds large fills); batches and score-only keep two rows per lane (two CTAs per SM).
+// Single pairs (full fill and score only) run the three-rows-per-lane geometry (96-row strips: a third fewer links in
+// the strip-to-strip chain that bounds large fills); batches keep two rows per lane (two or more CTAs per SM).
 int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs, const swb_scoring* scoring,
               int32_t* dH, int32_t* dP, int64_t pitch, int64_t pair_stride, int64_t* d_maxPos, int32_t* d_maxScore,
               int device, void* stream, const swb_tuning* tuning, bool store, const StripLink* link = nullptr)
 {
-    if (store && npairs == 1)
+    if (npairs == 1)
         return swb_tall::fill_impl(a, m, b, n, npairs, scoring, dH, dP, pitch, pair_stride, d_maxPos, d_maxScore, device, stream,
                                    tuning, store, link);
     return swb::fill_impl(a, m, b, n, npairs, scoring, dH, dP, pitch, pair_stride, d_maxPos, d_maxScore, device, stream,

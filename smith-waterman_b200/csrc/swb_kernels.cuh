@@ -422,7 +422,9 @@ struct Strip {
     int   mcols;                  // m
     int   lb[kR];                 // 16*(H - gap) of my rows' local column 0 (column-strip mode: H of the left GPU's
                                   // last column; otherwise 16*(0 - gap)): injected as the left neighbour of block 0
-    int   rmax[kR], rcol[kR];     // score-only: best clean 16*H of each of my rows and its first column
+    // score-only: best cell of each of my rows.  rbest = 16*H | (3 - column in its block) of the first column that reached
+    // the row's maximum, rmax = rbest | 15 (what a later block must exceed: strictly larger H), rcol = the STEP it was found in
+    int   rmax[kR], rcol[kR], rbest[kR];
     int   kmax;                   // full fill: largest key of my cells in columns 1..m (strip maximum; the writers have no
                                   // ALU slots to spare for it)
     // PROF: the score bytes of my rows' characters against codes 0..3 / 4..7, this step's four score bytes per row,
@@ -582,19 +584,22 @@ struct Strip {
                 // score only: remember the first column of this row that reaches its maximum
                 // (strict '>' keeps the earliest column, i.e. the earliest anti-diagonal of the row);
                 // branch-free -- the compute warp must not diverge
-                int v0 = h0, v1 = h1, v2 = h2, v3 = h3;
+                // The column inside the block rides in the low four bits of the value (3 - e: among equal H the first
+                // column is the larger key; four IMADs), one three-input maximum + one maximum find the block's best,
+                // and it replaces the row's best only if its H is strictly larger (compare against best | 15).
+                int v0 = addf(h0, 3 - kH7), v1 = addf(h1, 2 - kH7), v2 = addf(h2, 1 - kH7), v3 = addf(h3, 0 - kH7);
                 if (MODE != 0) {
                     const int c = 4 * j;
-                    v0 = (c >= 1 && c <= mcols) ? h0 : -1;
-                    v1 = (c + 1 >= 1 && c + 1 <= mcols) ? h1 : -1;
-                    v2 = (c + 2 >= 1 && c + 2 <= mcols) ? h2 : -1;
-                    v3 = (c + 3 >= 1 && c + 3 <= mcols) ? h3 : -1;
+                    v0 = (c >= 1 && c <= mcols) ? v0 : -1;
+                    v1 = (c + 1 >= 1 && c + 1 <= mcols) ? v1 : -1;
+                    v2 = (c + 2 >= 1 && c + 2 <= mcols) ? v2 : -1;
+                    v3 = (c + 3 >= 1 && c + 3 <= mcols) ? v3 : -1;
                 }
-                const int bm = max(max(v0, v1), max(v2, v3));
-                const int e = (v0 == bm) ? 0 : (v1 == bm) ? 1 : (v2 == bm) ? 2 : 3;
+                const int bm = max(__vimax3_s32(v0, v1, v2), v3);
                 const bool upd = bm > rmax[q];
-                rcol[q] = upd ? 4 * j + e : rcol[q];
-                rmax[q] = upd ? bm : rmax[q];
+                rbest[q] = upd ? bm : rbest[q];
+                rmax[q] = upd ? (bm | 15) : rmax[q];
+                rcol[q] = upd ? t : rcol[q];
             }
             u0 = h0; u1 = h1; u2 = h2; u3 = h3;          // the row above the next row
         }
@@ -1065,7 +1070,7 @@ __host__ __device__ constexpr size_t fill_smem_bytes(int wpc, int KT, bool store
 // STORE = false is the score-only variant: no staging, no writers, per-row best cells instead.
 // ---------------------------------------------------------------------------------
 template <int KT, bool STORE, bool PROF>
-__global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true), (KT == 64 && STORE) ? 1 : 2)
+__global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true), ((KT == 64 && STORE) || kR > 2) ? 1 : 2)
 fill_kernel(const FillParams p_in)
 {
     // Both instantiations are launched; the alphabet of b (counted on the device by selector_kernel, so that the call
@@ -1144,7 +1149,7 @@ fill_kernel(const FillParams p_in)
             const long long row = r0 + kR * lane + q;
             S.b4[q] = (row <= p.n) ? (unsigned)p.b[row - 1] * 0x01010101u : 0u;
             S.inv[q] = (row <= p.n) ? 0u : 0x01010101u;
-            S.hl[q] = kH7; S.rmax[q] = 0; S.rcol[q] = 0; S.kmax = 0;
+            S.hl[q] = kH7; S.rmax[q] = 15; S.rcol[q] = 0; S.rbest[q] = 0; S.kmax = 0;
             if constexpr (PROF) {
                 // score bytes of this row's character against the codes 0..7: match for its own code, mismatch for the
                 // others (the pad code and rows past n never match)
@@ -1232,9 +1237,10 @@ fill_kernel(const FillParams p_in)
 #pragma unroll
             for (int q = 0; q < kR; ++q) {
                 const long long row = r0 + kR * lane + q;
+                const int col = 4 * (S.rcol[q] - lane) + 3 - (S.rbest[q] & 15);      // step -> block, low bits -> column in it
                 if (row <= p.n)
-                    p.row_best[row] = ((unsigned long long)(unsigned)(S.rmax[q] >> 4) << 32) | (0xffffffffu - (unsigned)S.rcol[q]);
-                if (row <= p.n) mx = max(mx, S.rmax[q] >> 4);
+                    p.row_best[row] = ((unsigned long long)(unsigned)(S.rbest[q] >> 4) << 32) | (0xffffffffu - (unsigned)col);
+                if (row <= p.n) mx = max(mx, S.rbest[q] >> 4);
             }
             mx = __reduce_max_sync(0xffffffffu, mx);
             if (lane == 0 && mx > 0) { atomicMax(p.strip_max + strip, mx); atomicMax(p.gmax, mx); }

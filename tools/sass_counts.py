@@ -21,16 +21,18 @@ for l in out.split("\n"):
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m and name:
         funcs[name].append(m.group(2))
+FMA = ("IMAD", "IDP")
 ALU = ("VIADDMNMX", "VIMNMX3", "VIMNMX", "LOP3", "SEL", "ISETP", "IADD3", "VIADD", "SHF", "PRMT", "LEA", "IABS", "FLO", "POPC", "MOV", "CS2R", "R2P", "P2R", "PLOP3")
-FMA = ("IMAD",)
 LSU = ("SHFL", "LDS", "STS", "LDG", "STG", "LD", "ST", "CCTL", "ATOMS", "RED", "ATOMG")
-names = {"ILi64ELb1ELb1": "fill_kernel<64,store,profile>  (single pair, full fill)",
-         "ILi64ELb1ELb0": "fill_kernel<64,store,compare>  (single pair, > 8 letters)",
-         "ILi64ELb0ELb1": "fill_kernel<64,score-only,profile>",
-         "ILi32ELb1ELb1": "fill_kernel<32,store,profile>  (batch)"}
+names = {"swb_tall11fill_kernelILi64ELb1ELb1": "swb_tall::fill_kernel<64,store,look-up>  (single pair, full fill, 3 rows per lane)",
+         "swb_tall11fill_kernelILi64ELb1ELb0": "swb_tall::fill_kernel<64,store,compare>  (single pair, > 7 letters)",
+         "swb_tall11fill_kernelILi64ELb0ELb1": "swb_tall::fill_kernel<64,score-only,look-up>  (single pair)",
+         "3swb11fill_kernelILi64ELb0ELb1": "swb::fill_kernel<64,score-only,look-up>  (batch, 2 rows per lane)",
+         "3swb11fill_kernelILi32ELb1ELb1": "swb::fill_kernel<32,store,look-up>  (batch, 2 rows per lane)"}
+ROWS = {"swb_tall": 3, "3swb": 2}
 res, lines = {}, []
 for fn, ins in funcs.items():
-    key = next((k for k in names if k in fn and "fill_kernel" in fn), None)
+    key = next((k for k in names if k in fn), None)
     if not key:
         continue
     blocks, cur = [], []
@@ -47,19 +49,22 @@ for fn, ins in funcs.items():
     c = collections.Counter(b)
     # cells in the block: one VIMNMX3 per cell (profile) or three VIADDMNMX per cell (compare); a block holds whole
     # steps of cell arithmetic plus the shuffles / stores of the step that straddles its first branch
+    rows = 3 if "swb_tall" in fn else 2
     ncell = c["VIMNMX3"] if "Lb1EEE" in fn else c["VIADDMNMX"] / 3.0
-    steps = ncell / 8.0
+    if "Lb0ELb1EEE" in fn:                 # score-only also tracks the row maxima with VIMNMX3 (2 per row and step)
+        ncell = c["IDP"]
+    steps = ncell / (4.0 * rows)
     alu = sum(v for k, v in c.items() if k in ALU); fma = sum(v for k, v in c.items() if k in FMA)
     lsu = sum(v for k, v in c.items() if k in LSU)
-    cells = steps * 8
+    cells = ncell
     rec = {"block_instructions": len(b), "steps": steps, "alu_per_step": alu / steps, "fma_per_step": fma / steps,
            "lsu_per_step": lsu / steps, "total_per_step": len(b) / steps, "alu_ops_per_cell": alu / cells,
            "all_ops_per_cell": len(b) / cells, "mix": dict(c.most_common())}
     res[names[key]] = rec
-    lines.append(f"{names[key]}\n  fast interior block: {len(b)} instructions ~ {steps:.2f} steps of 8 cells\n"
+    lines.append(f"{names[key]}\n  fast interior block: {len(b)} instructions ~ {steps:.2f} steps\n"
                  f"  per step: ALU pipe {alu / steps:.1f}  FMA pipe {fma / steps:.1f}  LSU/MIO {lsu / steps:.1f}  total {len(b) / steps:.1f}\n"
                  f"  per cell: ALU {alu / cells:.2f}  all {len(b) / cells:.2f}\n  mix: {dict(c.most_common(14))}\n")
-so = res.get(names["ILi64ELb0ELb1"])
+so = res.get(names["swb_tall11fill_kernelILi64ELb0ELb1"])
 summary = {"score_only_alu_ops_per_cell": so["alu_ops_per_cell"] if so else None, "kernels": res,
            "source": "cuobjdump -sass of smith-waterman_b200/libswb200.so (tools/sass_counts.py)"}
 (ROOT / "profiles" / "r02_sass_counts.json").write_text(json.dumps(summary, indent=1))
