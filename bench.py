@@ -529,6 +529,7 @@ def run_single(args, torch, swb, dev, local):
         nbytes = cells_padded * 4
         hH = swb.host_alloc(nbytes)
         hP = swb.host_alloc(nbytes)
+        e2e_parity = None
         try:
             with swb.AlignContext(cols, rows, device=local) as ctx:
                 ctx.align(a, b, hH, hP)                      # warm-up (also faults in the pinned pages)
@@ -539,11 +540,34 @@ def run_single(args, torch, swb, dev, local):
                 barrier()
                 dt = (time.perf_counter() - t0) / args.e2e_steps
             assert (mp2, pl2) == (maxPos, plen), "host-buffer call disagrees with the device-resident call"
+            # what the caller received in HOST memory, against the oracle's digests (uploaded again for the arithmetic)
+            if g is not None:
+                import ctypes
+                import numpy as np
+                ncell = (rows + 1) * (cols + 1)
+                hHv = np.ctypeslib.as_array(ctypes.cast(hH, ctypes.POINTER(ctypes.c_int32)), shape=(ncell,))
+                hPv = np.ctypeslib.as_array(ctypes.cast(hP, ctypes.POINTER(ctypes.c_int32)), shape=(ncell,))
+                cH = torch.from_numpy(hHv).to(dev).view(rows + 1, cols + 1)
+                cP = torch.from_numpy(hPv).to(dev).view(rows + 1, cols + 1)
+                checked, bad = check_digests(g, cH, cP.abs(), 0, cols)
+                from oracle.digest import path_digest
+                neg = torch.nonzero(cP.view(-1) < 0).view(-1).cpu().numpy()
+                e2e_parity = {"digests_checked": checked, "digest_mismatches": bad,
+                              "path_cells_ok": bool(neg.size == g["path_len"] and path_digest(neg) == g["path_digest"])}
+                cH = cP = None
+                torch.cuda.empty_cache()
         finally:
             swb.host_free(hH); swb.host_free(hP)
+        packed = os.environ.get("SWB_PACKED_D2H", "") != "0" and nbytes >= (32 << 20)
+        d2h = (swb.packed_pitch(cols + 1) * (rows + 1) + 24) if packed else (2 * nbytes + 16)
         e2e = {"value": cols * rows / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": cols + rows,
-               "d2h_bytes_per_step": 2 * nbytes + 16, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-               "api": "swb_ctx_align (host a,b -> host H, P after backtrack, maxPos, path length)"}
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "host_bytes_delivered_per_step": 2 * nbytes + 16,
+               "transfer": ("packed: one byte per cell over PCIe (row step of H + P), expanded into the caller's int32 H and P "
+                            f"by {swb.host_threads()} host threads while later chunks are in flight (swb_pack.cu)"
+                            if packed else "plain int32 copies"),
+               "parity": e2e_parity,
+               "api": "swb_ctx_align (host a,b -> host int32 H, P after backtrack, maxPos, path length)"}
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -123,6 +123,29 @@ int32_t* swb_ctx_dH(swb_ctx* ctx);
 int32_t* swb_ctx_dP(swb_ctx* ctx);
 void swb_ctx_destroy(swb_ctx* ctx);
 
+/* Packed transfer of H and P (swb_pack.cu).  The reference's matrices are int32 in host memory
+ * (omp_smithW.c:203-216), so a device fill ends with 8 bytes per cell crossing PCIe -- 70 times the
+ * duration of the fill.  On the wire one byte per cell is enough: bits 7..3 = H[i][j] - H[i][j-1] + 16
+ * (the recurrence bounds the row step of H by gap .. match - gap, omp_smithW.c:331-388), bits 2..0 =
+ * P[i][j] + 3 (directions 0..3, negated on the path, omp_smithW.c:405-420).
+ *   swb_pack_rows_async  DEVICE: rows row0 .. row0+nrows-1, columns 0 .. cols-1 of dH/dP (row pitch `pitch`,
+ *                        column -1 counts as 0) -> d_packed (row pitch packed_pitch >= cols, a multiple of 4;
+ *                        swb_packed_pitch(cols) gives the canonical one).  *d_overflow (device int, zeroed by
+ *                        the caller) is set to 1 when a value does not fit; the packed bytes are then
+ *                        meaningless and the caller must copy the int32 matrices instead.
+ *   swb_expand_rows      HOST: packed rows -> int32 H and/or P (either may be NULL), bit-exact, on `threads`
+ *                        host threads (0 = swb_host_threads(): SWB_HOST_THREADS or the hardware concurrency).
+ * swb_ctx_align uses the pair for matrices of 32 MiB and more (SWB_PACKED_D2H=0 turns that off, =1 forces it):
+ * the packed bytes are copied in chunks and expanded while later chunks are in flight; the caller still receives
+ * the reference's int32 matrices.  A caller that only needs parts of H/P (say the rows a path crosses) can keep the
+ * packed form and expand just those rows. */
+int64_t swb_packed_pitch(int64_t cols);
+int  swb_host_threads(void);
+int  swb_pack_rows_async(const int32_t* dH, const int32_t* dP, int64_t pitch, int64_t row0, int64_t nrows, int64_t cols,
+                         unsigned char* d_packed, int64_t packed_pitch, int* d_overflow, int device, void* stream);
+int  swb_expand_rows(const unsigned char* packed, int64_t packed_pitch, int64_t nrows, int64_t cols,
+                     int32_t* H, int32_t* P, int64_t pitch, int threads);
+
 /* Score-only variant (no H/P stores): max score and maxPos with the reference
  * tie-break.  Replaces the -DSKIP_BACKTRACK style runs of the reference's
  * variants (omp_smithW-v1-refinedOrig.cpp:190-192) for callers that only need

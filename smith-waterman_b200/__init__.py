@@ -112,6 +112,10 @@ def _load() -> C.CDLL:
     L.swb_cigar_from_moves.argtypes = [vp, i64, C.c_char_p, C.c_size_t]; L.swb_cigar_from_moves.restype = i64
     L.swb_alignment_from_moves.argtypes = [vp, i64, vp, vp, i64, i64, C.c_char_p, C.c_char_p]
     L.swb_traceback_async.restype = C.c_int; L.swb_alignment_from_moves.restype = C.c_int
+    L.swb_packed_pitch.argtypes = [i64]; L.swb_packed_pitch.restype = i64
+    L.swb_host_threads.argtypes = []; L.swb_host_threads.restype = C.c_int
+    L.swb_pack_rows_async.argtypes = [vp, vp, i64, i64, i64, i64, vp, i64, vp, C.c_int, vp]; L.swb_pack_rows_async.restype = C.c_int
+    L.swb_expand_rows.argtypes = [vp, i64, i64, i64, vp, vp, i64, C.c_int]; L.swb_expand_rows.restype = C.c_int
     for name in ("swb_fill_pairs_async", "swb_shard_pairs", "swb_multi_create", "swb_multi_fill", "swb_multi_backtrack",
                  "swb_multi_align", "swb_multi_strips", "swb_multi_strip", "swb_multi_gather_host", "swb_fill_multi",
                  "swb_seq_count", "swb_seq_read", "swb_manifest_load", "swb_manifest_pair"):
@@ -437,6 +441,26 @@ def traceback_async(dP, pitch: int, startPos: int = 0, d_startPos=None, d_pathLe
     """backtrack that also writes the path's moves (device uint8 buffer, walk order; 1 UP, 2 LEFT, 3 DIAGONAL)"""
     _check(lib.swb_traceback_async(_ptr(dP), pitch, startPos, _ptr(d_startPos), _ptr(d_pathLen), _ptr(d_endPos),
                                    _ptr(d_moves), device, _stream_ptr(stream)))
+
+
+def packed_pitch(cols: int) -> int:
+    return int(lib.swb_packed_pitch(cols))
+
+
+def host_threads() -> int:
+    return int(lib.swb_host_threads())
+
+
+def pack_rows_async(dH, dP, pitch: int, row0: int, nrows: int, cols: int, d_packed, packed_pitch_: int, d_overflow,
+                    device: int = 0, stream=None) -> None:
+    """DEVICE: one byte per cell (row step of H + P) of rows row0 .. row0+nrows-1 (include/swb200.h, packed transfer)."""
+    _check(lib.swb_pack_rows_async(_ptr(dH), _ptr(dP), pitch, row0, nrows, cols, _ptr(d_packed), packed_pitch_,
+                                   _ptr(d_overflow), device, _stream_ptr(stream)))
+
+
+def expand_rows(packed, packed_pitch_: int, nrows: int, cols: int, H, P, pitch: int, threads: int = 0) -> None:
+    """HOST: packed rows -> int32 H and/or P (bit-exact)."""
+    _check(lib.swb_expand_rows(_ptr(packed), packed_pitch_, nrows, cols, _ptr(H), _ptr(P), pitch, threads))
 
 
 def cigar_from_moves(moves: bytes) -> str:

@@ -8,9 +8,20 @@
 #define SWB_NS swb_tall
 #define SWB_ROWS_PER_LANE 3
 #define SWB_FILL_ONLY 1
+#ifndef SWB_TALL_HALF_SKEW
+#define SWB_TALL_HALF_SKEW 1
+#endif
+#undef SWB_HALF_SKEW
+#define SWB_HALF_SKEW SWB_TALL_HALF_SKEW
 #include "swb_kernels.cuh"              // namespace swb_tall: three rows per lane (single large pairs)
 #undef SWB_NS
+#undef SWB_HALF_SKEW
+#define SWB_NS swb_wide
+#define SWB_HALF_SKEW 0
+#include "swb_kernels.cuh"              // namespace swb_wide: three rows per lane, full skew (single pairs far wider than tall)
+#undef SWB_NS
 #undef SWB_FILL_ONLY
+#undef SWB_HALF_SKEW
 
 #include <algorithm>
 #include <cstdio>
@@ -116,11 +127,22 @@ struct StripLink {                         // column-strip mode (nullptr members
 
 }  // namespace
 
+// swb_pack.cu: chunked copy of packed rows with the host-side expansion running beside it
+namespace swb_packed {
+int copy_and_expand(const unsigned char* d_packed, unsigned char* h_packed, long long packed_pitch, long long nrows, long long cols,
+                    int32_t* H, int32_t* P, long long pitch, cudaStream_t st, int device, int threads, int nchunks);
+}
+
 // The fill's host side, once per kernel geometry (see swb_fill_impl.inc)
 namespace swb {
 #include "swb_fill_impl.inc"
 }
 namespace swb_tall {
+#define SWB_SINGLE_ONLY 1
+#include "swb_fill_impl.inc"
+#undef SWB_SINGLE_ONLY
+}
+namespace swb_wide {
 #define SWB_SINGLE_ONLY 1
 #include "swb_fill_impl.inc"
 #undef SWB_SINGLE_ONLY
@@ -132,10 +154,16 @@ namespace {
 //   dH/dP + k*pair_stride; d_maxPos / d_maxScore hold npairs entries.  store == false: score only.
 // Single pairs (full fill and score only) run the three-rows-per-lane geometry (96-row strips: a third fewer links in
 // the strip-to-strip chain that bounds large fills); batches keep two rows per lane (two or more CTAs per SM).
+// The half skew of swb_tall trades a 35 % longer step (two shuffle rounds) for a 45 % shorter strip-to-strip lag; a
+// matrix more than three times wider than tall has few strips and long rows, so the step dominates: full skew there
+// (measured, 2 000 000 columns x 1000 rows: 52.5 ms full skew, 69.4 ms half skew; 1000 x 2 000 000: 112 ms vs 75 ms).
 int fill_impl(const char* a, int64_t m, const char* b, int64_t n, int64_t npairs, const swb_scoring* scoring,
               int32_t* dH, int32_t* dP, int64_t pitch, int64_t pair_stride, int64_t* d_maxPos, int32_t* d_maxScore,
               int device, void* stream, const swb_tuning* tuning, bool store, const StripLink* link = nullptr)
 {
+    if (npairs == 1 && m > 3 * n)
+        return swb_wide::fill_impl(a, m, b, n, npairs, scoring, dH, dP, pitch, pair_stride, d_maxPos, d_maxScore, device, stream,
+                                   tuning, store, link);
     if (npairs == 1)
         return swb_tall::fill_impl(a, m, b, n, npairs, scoring, dH, dP, pitch, pair_stride, d_maxPos, d_maxScore, device, stream,
                                    tuning, store, link);
@@ -481,9 +509,13 @@ struct swb_ctx {
     int device = 0;
     int64_t m = 0, n = 0;
     int32_t* dH = nullptr; int32_t* dP = nullptr;
-    long long* d_scalars = nullptr;        // [0] maxPos, [1] pathLen
+    long long* d_scalars = nullptr;        // [0] maxPos, [1] pathLen, [2] packed-transfer overflow flag
     cudaStream_t st = nullptr;
+    // packed copy-back (swb_pack.cu): one byte per cell on the device and in pinned host memory, allocated on first use
+    unsigned char* d_packed = nullptr; unsigned char* h_packed = nullptr;
+    bool packed_tried = false;
 };
+
 
 int swb_ctx_create(swb_ctx** out, int64_t m, int64_t n, int device)
 {
@@ -496,7 +528,7 @@ int swb_ctx_create(swb_ctx** out, int64_t m, int64_t n, int device)
     cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->dH), bytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->dP), bytes);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_scalars), 2 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_scalars), 3 * sizeof(long long));
     if (e != cudaSuccess) { int rc = cuda_fail(e, "swb_ctx_create allocation", __LINE__); swb_ctx_destroy(c); return rc; }
     *out = c;
     return SWB_OK;
@@ -509,12 +541,24 @@ void swb_ctx_destroy(swb_ctx* c)
     if (c->dH) cudaFree(c->dH);
     if (c->dP) cudaFree(c->dP);
     if (c->d_scalars) cudaFree(c->d_scalars);
+    if (c->d_packed) cudaFree(c->d_packed);
+    if (c->h_packed) cudaFreeHost(c->h_packed);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
 
 int32_t* swb_ctx_dH(swb_ctx* c) { return c ? c->dH : nullptr; }
 int32_t* swb_ctx_dP(swb_ctx* c) { return c ? c->dP : nullptr; }
+
+// Packed copy-back is used for matrices of at least this many bytes each (below it the plain copies take well under a
+// millisecond); SWB_PACKED_D2H=0 turns it off, =1 forces it for every size.
+static bool packed_wanted(size_t bytes)
+{
+    static const int mode = [] { const char* s = std::getenv("SWB_PACKED_D2H"); return s ? std::atoi(s) : -1; }();
+    if (mode == 0) return false;
+    if (mode > 0) return true;
+    return bytes >= ((size_t)32 << 20);
+}
 
 int swb_ctx_align(swb_ctx* c, const char* a, const char* b, const swb_scoring* scoring,
                   int32_t* H, int32_t* P, int64_t* maxPos, int64_t* path_len, int do_backtrack)
@@ -523,11 +567,23 @@ int swb_ctx_align(swb_ctx* c, const char* a, const char* b, const swb_scoring* s
     DeviceGuard guard(c->device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     const size_t bytes = (size_t)(c->m + 1) * (size_t)(c->n + 1) * sizeof(int32_t);
+    const int64_t ppitch = swb_packed_pitch(c->m + 1);
+    bool packed = (H || P) && packed_wanted(bytes);
+    if (packed && !c->packed_tried) {
+        // (a context whose packed buffers cannot be had keeps working with the plain copies)
+        c->packed_tried = true;
+        const size_t pbytes = (size_t)ppitch * (size_t)(c->n + 1);
+        if (cudaMalloc(reinterpret_cast<void**>(&c->d_packed), pbytes) != cudaSuccess) { c->d_packed = nullptr; cudaGetLastError(); }
+        else if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_packed), pbytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(c->d_packed); c->d_packed = nullptr; c->h_packed = nullptr;
+        }
+    }
+    packed = packed && c->d_packed && c->h_packed;
     int rc = swb_fill_async(a, c->m, b, c->n, scoring, c->dH, c->dP, c->m + 1,
                             reinterpret_cast<int64_t*>(c->d_scalars), nullptr, c->device, c->st, nullptr);
     if (rc != SWB_OK) return rc;
-    // H does not change any more: start its copy-back before the backtrack
-    if (H) SWB_CUDA(cudaMemcpyAsync(H, c->dH, bytes, cudaMemcpyDeviceToHost, c->st));
+    // plain copies: H does not change any more, start its copy-back before the backtrack
+    if (H && !packed) SWB_CUDA(cudaMemcpyAsync(H, c->dH, bytes, cudaMemcpyDeviceToHost, c->st));
     if (do_backtrack) {
         rc = swb_backtrack_async(c->dP, c->m + 1, 0, reinterpret_cast<int64_t*>(c->d_scalars),
                                  reinterpret_cast<int64_t*>(c->d_scalars + 1), c->device, c->st);
@@ -535,12 +591,32 @@ int swb_ctx_align(swb_ctx* c, const char* a, const char* b, const swb_scoring* s
     } else {
         SWB_CUDA(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(long long), c->st));
     }
-    if (P) SWB_CUDA(cudaMemcpyAsync(P, c->dP, bytes, cudaMemcpyDeviceToHost, c->st));
-    long long sc2[2] = {0, 0};
-    SWB_CUDA(cudaMemcpyAsync(sc2, c->d_scalars, sizeof sc2, cudaMemcpyDeviceToHost, c->st));
-    SWB_CUDA(cudaStreamSynchronize(c->st));
-    if (maxPos) *maxPos = sc2[0];
-    if (path_len) *path_len = sc2[1];
+    long long sc3[3] = {0, 0, 0};
+    if (packed) {
+        // one byte per cell over PCIe, expanded into the caller's int32 matrices on the host (swb_pack.cu)
+        SWB_CUDA(cudaMemsetAsync(c->d_scalars + 2, 0, sizeof(long long), c->st));
+        rc = swb_pack_rows_async(c->dH, c->dP, c->m + 1, 0, c->n + 1, c->m + 1, c->d_packed, ppitch,
+                                 reinterpret_cast<int*>(c->d_scalars + 2), c->device, c->st);
+        if (rc != SWB_OK) return rc;
+        SWB_CUDA(cudaMemcpyAsync(sc3, c->d_scalars, sizeof sc3, cudaMemcpyDeviceToHost, c->st));
+        SWB_CUDA(cudaStreamSynchronize(c->st));
+        if (sc3[2] == 0) {
+            rc = swb_packed::copy_and_expand(c->d_packed, c->h_packed, ppitch, c->n + 1, c->m + 1, H, P, c->m + 1, c->st,
+                                             c->device, 0, 24);
+            if (rc != SWB_OK) return rc;
+        } else {
+            // some row step of H or some P value does not fit the byte format (exotic scoring): plain copies
+            if (H) SWB_CUDA(cudaMemcpyAsync(H, c->dH, bytes, cudaMemcpyDeviceToHost, c->st));
+            if (P) SWB_CUDA(cudaMemcpyAsync(P, c->dP, bytes, cudaMemcpyDeviceToHost, c->st));
+            SWB_CUDA(cudaStreamSynchronize(c->st));
+        }
+    } else {
+        if (P) SWB_CUDA(cudaMemcpyAsync(P, c->dP, bytes, cudaMemcpyDeviceToHost, c->st));
+        SWB_CUDA(cudaMemcpyAsync(sc3, c->d_scalars, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+        SWB_CUDA(cudaStreamSynchronize(c->st));
+    }
+    if (maxPos) *maxPos = sc3[0];
+    if (path_len) *path_len = sc3[1];
     return SWB_OK;
 }
 

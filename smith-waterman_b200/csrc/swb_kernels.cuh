@@ -115,6 +115,22 @@ constexpr int kWaitSteps = SWB_WAIT_STEPS;   // steps per poll of the strip abov
 #ifndef SWB_WAIT_STEPS_SINGLE
 #define SWB_WAIT_STEPS_SINGLE 8        // measured: 45000x45000 4.99 -> 4.89 ms, 100000x100000 18.7 -> 18.5 ms; the batch and
 #endif                                 // score-only instantiations are 2 % faster with 4
+// Half skew (SWB_HALF_SKEW, the single-pair geometry): lane l trails lane l-1 by TWO columns instead of four.  A step
+// still covers four columns of each of the lane's rows, but in two halves: the row above the first two columns was
+// produced by the lane above in the second half of ITS previous step, the row above the last two in the first half of
+// its CURRENT step (one pair of shuffles after each half).  Lane 31 then trails lane 0 by 16 steps instead of 31, so a
+// strip can follow the strip above after 16 + 8 steps instead of 32 + 8: the strip-to-strip chain that bounds large
+// fills shrinks by 40 % for the same instructions per step.  Odd lanes work on columns
+// 4j+2 .. 4j+5: the packed copy of a exists twice, the second copy shifted by two columns.
+#ifndef SWB_HALF_SKEW
+#define SWB_HALF_SKEW 0
+#endif
+constexpr bool kHS        = SWB_HALF_SKEW != 0;
+constexpr int kSkewCols   = kHS ? 2 : 4;           // columns a lane trails the lane above
+constexpr int kSkewSteps  = kHS ? 16 : 31;         // steps lane 31 trails lane 0 (rounded up)
+constexpr int kInOfs      = kHS ? -15 : 1;         // entry of the strip above that step t loads: t + kInOfs (entry x = the
+                                                   // block lane 31 of the strip above produced in its step x + 31)
+constexpr int kFirstEntry = kHS ? -16 : 0;         // first entry a strip needs (half skew: the row above columns 0 and 1)
 constexpr int kAPad     = 64;          // leading pad words of the packed copy of a
 // Score look-up (PROF instantiations): when b uses at most kMaxLetters distinct byte values and the scores fit a signed
 // byte, the substitution scores are not derived from the characters with a compare and a select per cell.  The packed
@@ -151,6 +167,8 @@ constexpr int kHandOff = 5;            // P code of local column 0 in column-str
 
 struct FillParams {
     const unsigned* a4;      // a4[kAPad + j] = a[4j-1 .. 4j+2] (block j; 0 outside [0,m))
+    const unsigned* a4s;     // the same shifted by two columns: a4s[kAPad + j] = a[4j+1 .. 4j+4] (half skew: odd lanes)
+    int             in_last; // last entry of the row above a strip that holds a column <= m
     const unsigned char* b;  // n bytes, device
     int32_t*        H;
     int32_t*        P;
@@ -317,10 +335,12 @@ __global__ void prep_kernel(const unsigned char* __restrict__ a, long long m, lo
 {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
-    for (long long x = tid; x < nwords * npairs; x += nth) {
-        const long long pair = x / nwords, w = x % nwords;
+    // (two copies: the second one, nwords * npairs words further on, is shifted by two columns -- half skew)
+    for (long long x = tid; x < 2 * nwords * npairs; x += nth) {
+        const long long y = x % (nwords * npairs), shift = 2 * (x / (nwords * npairs));
+        const long long pair = y / nwords, w = y % nwords;
         const unsigned char* ap = a + pair * m;
-        const long long base = 4 * (w - kAPad) - 1;
+        const long long base = 4 * (w - kAPad) - 1 + shift;
         unsigned word = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -380,10 +400,11 @@ __global__ void selector_kernel(const unsigned char* __restrict__ a, long long m
     if (s_n > kMaxLetters) return;         // the characters stay in a4: the character-compare instantiation runs
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
-    for (long long x = tid; x < nwords * npairs; x += nth) {
-        const long long pair = x / nwords, w = x % nwords;
+    for (long long x = tid; x < 2 * nwords * npairs; x += nth) {
+        const long long y = x % (nwords * npairs), shift = 2 * (x / (nwords * npairs));
+        const long long pair = y / nwords, w = y % nwords;
         const unsigned char* ap = a + pair * m;
-        const long long base = 4 * (w - kAPad) - 1;
+        const long long base = 4 * (w - kAPad) - 1 + shift;
         unsigned word = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -639,6 +660,148 @@ struct Strip {
         A2 = l0 ? v.z : n2;
         A3 = l0 ? v.w : n3;
     }
+
+    // The same step with HALF SKEW (kHS): my columns are c0 = 4t - 2*lane .. c0 + 3.  First half (c0, c0+1): the row
+    // above is A0, A1 (shuffled at the end of the previous step); second half (c0+2, c0+3): the row above is what the
+    // lane above produced in the first half of THIS step.  Lane 0 takes both from entry t + kInOfs of the strip above
+    // (.xy now, .zw for the first half of the next step).  dgp = the row above at column c0 - 1.
+    template <int MODE, int I>
+    __device__ __forceinline__ void step_hs(const int t, const unsigned next_word,
+                                            const unsigned in_g, const unsigned in_w, const int want, const int want_w,
+                                            const unsigned out_g, const unsigned out_w, const int otag, const int otag_w)
+    {
+        constexpr bool LAST = (I == kGroup - 1);
+        const int c0 = 4 * t - 2 * lane;
+        int4 v;
+        if (MODE & 2) {
+            v = make_int4(0, kH7, kH7, kH7);
+            if (has_in && t + kInOfs <= jmax) v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
+        } else {
+            v = LAST ? lds_volatile_int4<0>(in_w) : lds_volatile_int4<16 * (I + 1)>(in_g);
+        }
+        int hA0[kR], hA1[kR], kA0[kR], kA1[kR];
+        int nA0, nA1, nB2, nB3;
+        // ---------------- first half: columns c0, c0 + 1
+        {
+            int u0 = A0, u1 = A1, dg = dgp;
+#pragma unroll
+            for (int q = 0; q < kR; ++q) {
+                int D0 = dg, D1 = u0, L0 = hl[q];
+                if (MODE & 1) {
+                    // head of a strip in column-strip mode: columns <= 0 cannot take the diagonal, and the boundary value
+                    // enters as the left neighbour of column 0
+                    D0 = (c0 <= 0) ? kSNeg : D0; D1 = (c0 + 1 <= 0) ? kSNeg : D1;
+                    L0 = (c0 == 0) ? lb[q] : L0;
+                }
+                int t0, t1;
+                if constexpr (PROF) {
+                    const int d0 = __dp4a(sb[q], 16, D0), d1 = __dp4a(sb[q], 16 << 8, D1);
+                    const int v0 = addf(u0, gu), v1 = addf(u1, gu);
+                    t0 = __vimax3_s32(d0, v0, kTieNone);
+                    t1 = __vimax3_s32(d1, v1, kTieNone);
+                } else {
+                    const int p0 = __viaddmax_s32(D0, s[q][0], kTieNone);
+                    const int p1 = __viaddmax_s32(D1, s[q][1], kTieNone);
+                    t0 = __viaddmax_s32(u0, gu, p0);
+                    t1 = __viaddmax_s32(u1, gu, p1);
+                }
+                dg = hl[q];                              // the row above the next row at column c0 - 1
+                const int k0 = __viaddmax_s32(L0, gl, t0);
+                const int h0 = (k0 & ~15) | h7r;
+                if (q == kR - 1) nA0 = __shfl_up_sync(0xffffffffu, h0, 1);
+                const int k1 = __viaddmax_s32(h0, gl, t1);
+                const int h1 = (k1 & ~15) | h7r;
+                if (q == kR - 1) nA1 = __shfl_up_sync(0xffffffffu, h1, 1);
+                hA0[q] = h0; hA1[q] = h1; kA0[q] = k0; kA1[q] = k1;
+                u0 = h0; u1 = h1;
+            }
+        }
+        // ---------------- second half: columns c0 + 2, c0 + 3
+        const bool l0 = (lane == 0);
+        const int b2 = l0 ? (PROF ? ((v.x & ~15) | h7r) : (v.x & ~15)) : nA0;
+        const int b3 = l0 ? v.y : nA1;
+        int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+        {
+            int u2 = b2, u3 = b3, dg = A1;               // the row above at column c0 + 1
+#pragma unroll
+            for (int q = 0; q < kR; ++q) {
+                int D2 = dg, D3 = u2, L2 = hA1[q];
+                if (MODE & 1) {
+                    D2 = (c0 + 2 <= 0) ? kSNeg : D2; D3 = (c0 + 3 <= 0) ? kSNeg : D3;
+                    L2 = (c0 + 2 == 0) ? lb[q] : L2;
+                }
+                int t2, t3;
+                if constexpr (PROF) {
+                    const int d2 = __dp4a(sb[q], 16 << 16, D2), d3 = __dp4a(sb[q], 16 << 24, D3);
+                    const int v2 = addf(u2, gu), v3 = addf(u3, gu);
+                    t2 = __vimax3_s32(d2, v2, kTieNone);
+                    t3 = __vimax3_s32(d3, v3, kTieNone);
+                } else {
+                    const int p2 = __viaddmax_s32(D2, s[q][2], kTieNone);
+                    const int p3 = __viaddmax_s32(D3, s[q][3], kTieNone);
+                    t2 = __viaddmax_s32(u2, gu, p2);
+                    t3 = __viaddmax_s32(u3, gu, p3);
+                }
+                dg = hA1[q];
+                const int k2 = __viaddmax_s32(L2, gl, t2);
+                const int h2 = (k2 & ~15) | h7r;
+                if (q == kR - 1) nB2 = __shfl_up_sync(0xffffffffu, h2, 1);
+                const int k3 = __viaddmax_s32(h2, gl, t3);
+                const int h3 = (k3 & ~15) | h7r;
+                if (q == kR - 1) nB3 = __shfl_up_sync(0xffffffffu, h3, 1);
+                hl[q] = h3;
+                const int k0 = kA0[q], k1 = kA1[q], h0 = hA0[q], h1 = hA1[q];
+                if (STORE && SWB_KMAXC) {
+                    int e0 = k0, e1 = k1, e2 = k2, e3 = k3;
+                    if (MODE & 1) { e0 = (c0 == 0) ? 0 : e0; e2 = (c0 + 2 == 0) ? 0 : e2; }       // column 0 (columns < 0 hold NONE)
+                    if (MODE & 2) {
+                        e0 = (c0 <= mcols) ? e0 : 0;
+                        e1 = (c0 + 1 <= mcols) ? e1 : 0;
+                        e2 = (c0 + 2 <= mcols) ? e2 : 0;
+                        e3 = (c0 + 3 <= mcols) ? e3 : 0;
+                    }
+                    kmax = __vimax3_s32(__vimax3_s32(kmax, e0, e1), e2, e3);
+                }
+                if (STORE) {
+                    if (q == 0) sts_int4<0>(sa, k0, k1, k2, k3);
+                    if (q == 1) sts_int4<kRowInts * 4>(sa, k0, k1, k2, k3);
+                    if (q == 2) sts_int4<2 * kRowInts * 4>(sa, k0, k1, k2, k3);
+                    if (q == 3) sts_int4<3 * kRowInts * 4>(sa, k0, k1, k2, k3);
+                } else {
+                    // score only: see step()
+                    int v0 = addf(h0, 3 - kH7), v1 = addf(h1, 2 - kH7), v2 = addf(h2, 1 - kH7), v3 = addf(h3, 0 - kH7);
+                    if (MODE != 0) {
+                        v0 = (c0 >= 1 && c0 <= mcols) ? v0 : -1;
+                        v1 = (c0 + 1 >= 1 && c0 + 1 <= mcols) ? v1 : -1;
+                        v2 = (c0 + 2 >= 1 && c0 + 2 <= mcols) ? v2 : -1;
+                        v3 = (c0 + 3 >= 1 && c0 + 3 <= mcols) ? v3 : -1;
+                    }
+                    const int bm = max(__vimax3_s32(v0, v1, v2), v3);
+                    const bool upd = bm > rmax[q];
+                    rbest[q] = upd ? bm : rbest[q];
+                    rmax[q] = upd ? (bm | 15) : rmax[q];
+                    rcol[q] = upd ? t : rcol[q];
+                }
+                u2 = h2; u3 = h3;
+                if (q == kR - 1) { o0 = h0; o1 = h1; o2 = h2; o3 = h3; }
+            }
+        }
+        dgp = b3;                                        // the row above at column c0 + 3 = before the next step's first column
+        if (STORE) sa = ((sa + 16u) & (unsigned)(KT * 16 - 1)) | sa_base;
+        // ---------------- hand my last row to the next strip (lane 31 only) ----------------
+        {
+            const int4 o = make_int4(PROF ? (o0 ^ (LAST ? otag_w : otag)) : (o0 | (LAST ? otag_w : otag)), o1, o2, o3);
+            if (LAST) sts_volatile_int4_if<0>(out_w, o, out_ring);
+            else      sts_volatile_int4_if<16 * I>(out_g, o, out_ring);
+            st_cg_int4_if<16 * I>(gout, o, out_glob);
+        }
+        // ---------------- scores of the next step ----------------
+        if constexpr (PROF) lookup(next_word);
+        else                scores(next_word);
+        // ---------------- the row above the first half of the next step ----------------
+        A0 = l0 ? v.z : nB2;
+        A1 = l0 ? v.w : nB3;
+    }
 };
 
 // Flags live in shared memory and are passed as 32-bit shared addresses.  Ordering between
@@ -653,15 +816,23 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 {
     const int lane = S.lane;
     trace_stamp(p, strip, 0, lane);
-    unsigned cur[kGroup + 1], nxt[kGroup];
+    // packed characters / selector words: this group's, the next group's, and the one after (loaded two groups = ~4000
+    // clk ahead: under the writers' store traffic a global load takes far longer than an idle L2 hit, and one group of
+    // distance left the warp waiting 300-400 clk per group for these eight words)
+    constexpr bool kPf2 = kHS;     // (the two-row geometry runs two CTAs per SM and has no registers for the third set)
+    unsigned cur[kGroup + 1], nxt[kGroup], nx2[kGroup];
 #pragma unroll
-    for (int i = 0; i < kGroup; ++i) cur[i] = __ldg(aw + i);
+    for (int i = 0; i < kGroup; ++i) { cur[i] = __ldg(aw + i); nxt[i] = __ldg(aw + kGroup + i); }
 
-    // first input block (block 0 -> ring index 32, epoch 0 -> tag 1); all lanes poll
+    // first input entry (entry x -> ring index (x+32)&63, epoch 0 -> tag 1); all lanes poll.  Half skew: entry -16 holds
+    // the row above columns -2 .. 1; its .zw is the row above the first half of step 0.
     if (S.has_in) {
-        int4 v = lds_volatile_int4<16 * 32>(S.ring_in);
-        while ((v.x & 3) != 1) { if (SWB_X_GATESLEEP > 0) __nanosleep(SWB_X_GATESLEEP); v = lds_volatile_int4<16 * 32>(S.ring_in); }
-        if (lane == 0) { S.A0 = (v.x & ~15) | S.kH7; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w; }
+        int4 v = lds_volatile_int4<16 * (32 + kFirstEntry)>(S.ring_in);
+        while ((v.x & 3) != 1) { if (SWB_X_GATESLEEP > 0) __nanosleep(SWB_X_GATESLEEP); v = lds_volatile_int4<16 * (32 + kFirstEntry)>(S.ring_in); }
+        if (lane == 0) {
+            if (kHS) { S.A0 = v.z; S.A1 = v.w; S.dgp = v.y; }
+            else     { S.A0 = (v.x & ~15) | S.kH7; S.A1 = v.y; S.A2 = v.z; S.A3 = v.w; }
+        }
     }
     trace_stamp(p, strip, 1, lane);
 #ifdef SWB_X_CLKTRACE
@@ -669,11 +840,11 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 #endif
     // (with the score look-up a NUL byte in b needs no care: positions outside a carry the pad code, which matches no row)
     const bool forced = (STORE && p.left_in != nullptr) || (!PROF && opaque(*p.nul_flag) != 0);
-    if constexpr (PROF) S.lookup(cur[0]);
-    else if (forced)    S.head_fix(cur[0], -lane);
-    else                S.scores(cur[0]);
+    if constexpr (PROF)    S.lookup(cur[0]);
+    else if (forced && !kHS) S.head_fix(cur[0], -lane);
+    else                   S.scores(cur[0]);
 
-    const int gtail = (p.jmax - 8) >> 3;          // groups g <= gtail: t+1 <= jmax for all their steps
+    const int gtail = (p.in_last - 7 - kInOfs) >> 3;      // groups g <= gtail: every entry their steps load exists (<= in_last)
     int known_drained = 0, known_consumed = 0;
 #ifdef SWB_X_GROUPTRACE
     long long dbg_pre = 0, dbg_steps = 0, dbg_post = 0, dbg_n = 0, dbg_e_steps = 0, dbg_e_other = 0, dbg_drain = 0, dbg_cons = 0;
@@ -705,9 +876,11 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         const long long gd1 = clock64();
 #endif
         // ---- hand-off ring space (blocks up to t0+7-31 are written in this group)
-        if (ring_consumer && t0 - (kRing + 16) > known_consumed) {
+        // (this group writes entries up to t0 + 7 - 31 over entries kRing older; at its group start c the consumer has
+        //  consumed the entries up to c + kInOfs - 1)
+        if (ring_consumer && t0 - (kRing + 15 + kInOfs) > known_consumed) {
             int c;
-            do { c = lds_volatile_int(consumed_out); } while (c < t0 - (kRing + 16));
+            do { c = lds_volatile_int(consumed_out); } while (c < t0 - (kRing + 15 + kInOfs));
             known_consumed = c;
         }
 #ifdef SWB_X_GROUPTRACE
@@ -716,14 +889,16 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         sts_volatile_int_if(consumed_in, t0, S.has_in & (lane == 0 ? 1 : 0));
         // ---- sequence words of the next group
 #pragma unroll
-        for (int i = 0; i < kGroup; ++i) nxt[i] = __ldg(aw + t0 + kGroup + i);
-        cur[kGroup] = nxt[0];
+        for (int i = 0; i < kGroup; ++i) nx2[i] = __ldg(aw + t0 + (kPf2 ? 2 : 1) * kGroup + i);
+        cur[kGroup] = kPf2 ? nxt[0] : nx2[0];
 
         // consumer side: block t -> ring index (t+32)&63, epoch ((t+32)>>6)&1
-        const unsigned in_g  = S.ring_in + 16u * (unsigned)((t0 + 32) & (kRing - 1));
-        const unsigned in_w  = S.ring_in + 16u * (unsigned)((t0 + 40) & (kRing - 1));
-        const int   want     = 1 + (((t0 + 32) >> kRingLog) & 1);
-        const int   want_w   = 1 + (((t0 + 40) >> kRingLog) & 1);
+        // (step t0 + I loads entry t0 + I + kInOfs = ring index in_g + I + 1)
+        constexpr int kRS = 32 + kInOfs - 1;
+        const unsigned in_g  = S.ring_in + 16u * (unsigned)((t0 + kRS) & (kRing - 1));
+        const unsigned in_w  = S.ring_in + 16u * (unsigned)((t0 + kRS + 8) & (kRing - 1));
+        const int   want     = 1 + (((t0 + kRS) >> kRingLog) & 1);
+        const int   want_w   = 1 + (((t0 + kRS + 8) >> kRingLog) & 1);
         // producer side: block t-31 -> ring index (t+1)&63, epoch ((t+1)>>6)&1 (= its (j+32) form)
         const unsigned out_g = S.ring_out + 16u * (unsigned)((t0 & (kRing - 1)) + 1);
         const unsigned out_w = S.ring_out + 16u * (unsigned)((t0 + 8) & (kRing - 1));
@@ -739,8 +914,8 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         // steps of extra lag behind the producer and saves a third of every step.
 #define SWB_WAIT(H)                                                                                       \
         if (S.has_in) {                                                                                   \
-            const int xb = min(t0 + kW * ((H) + 1), p.jmax);                                      \
-            if (xb > t0 + kW * (H)) wait_block(S.ring_in, xb);                                    \
+            const int xb = min(t0 + kW * ((H) + 1) + kInOfs - 1, p.in_last);                      \
+            if (xb > t0 + kW * (H) + kInOfs - 1) wait_block(S.ring_in, xb);                       \
         }
         // the same for a group that ends before jmax: block t0+4 sits four entries after block t0 (no wrap: t0 is a
         // multiple of 8) in the same epoch, block t0+8 is the entry the last step polls anyway
@@ -749,7 +924,8 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
             if (kW == 4 && (H) == 0) { while ((lds_volatile_int(in_g + 64u) & 3) != want) { } }  \
             else                             { while ((lds_volatile_int(in_w) & 3) != want_w) { } }       \
         }
-#define SWB_STEP(E, I) S.template step<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w)
+#define SWB_STEP(E, I) { if constexpr (kHS) S.template step_hs<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w); \
+                         else               S.template step<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w); }
         // forced = b holds a NUL byte, or column-strip mode (boundary injection): head and tail steps differ.
         // Otherwise a full fill runs the interior step everywhere; score only still masks the columns past m.
 #define SWB_GROUP(M, W) { W(0) SWB_STEP(M, 0); SWB_STEP(M, 1); SWB_STEP(M, 2); SWB_STEP(M, 3);       \
@@ -774,7 +950,7 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
 #endif
         S.gout += kGroup;
 #pragma unroll
-        for (int i = 0; i < kGroup; ++i) cur[i] = nxt[i];
+        for (int i = 0; i < kGroup; ++i) { cur[i] = kPf2 ? nxt[i] : nx2[i]; nxt[i] = nx2[i]; }
         // ---- publish the staged group to the writers
         __syncwarp();
         if (STORE) sts_volatile_int_if(staged, g + 1, lane == 0 ? 1 : 0);
@@ -817,10 +993,10 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
     const long long row = r0 + rho;
     const bool myrow = lane < kWRows && row <= p.n;
     const int ph = (int)((row * p.pitch) & 31);
-    const int d  = (cl + ((31 - ph) >> 2)) >> 3;
+    const int d  = (kSkewCols * cl + 31 - ph) >> 5;               // (lane cl has finished column 32r + 31 - kSkewCols*cl by the end of group r)
     const int E  = 32 * d + ph;
     const long long G0 = row * p.pitch - E;                      // multiple of 32
-    const int F  = (8 * cl - E) & (kRowInts - 1);                // ring index of column c is (c + 8*cl) mod kRowInts
+    const int F  = ((4 + kSkewCols) * cl - E) & (kRowInts - 1);   // ring index of column c is (c + (4 + kSkewCols)*cl) mod kRowInts
     const unsigned long long hb = (unsigned long long)(p.H + G0);
     if (lane < kWRows) rowtab[lane] = make_int4((int)(unsigned)hb, (int)(unsigned)(hb >> 32), F, E);
     // the same for the fast path: byte offset of the row's segment base from the strip's first row (fits 32 bits:
@@ -843,10 +1019,55 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #ifdef SWB_X_WRITERTRACE
     long long dw_wait = 0, dw_work = 0, dw_n = 0;
 #endif
+#ifndef SWB_WRITER_WIDE
+#define SWB_WRITER_WIDE 0              // 1: interior rounds are flushed two at a time: 64 columns = 256 contiguous bytes per row visit
+#endif
     for (int r = 0; r < rounds; ++r) {
 #ifdef SWB_X_WRITERTRACE
         const long long wc0 = clock64();
 #endif
+        if (SWB_WRITER_WIDE && KT == 64 && (r & 1) == 0 && r + 1 < rounds && nvalid == kWRows &&
+            (32 * r - Emax >= (p.left_in != nullptr ? 1 : 0)) && (32 * (r + 1) + 31 - Emin <= m - (p.right_out != nullptr ? 1 : 0))) {
+            // Two interior rounds at once.  The store pattern, not the instruction count, bounds the writers: a row
+            // visit of one 128-byte line per matrix opens a DRAM page for 128 bytes (tools/ubench_pattern.cu: 4.4 TB/s,
+            // 5.2 TB/s with two lines per visit).  One warp-wide 8-byte store covers the 64 columns = two adjacent lines
+            // of ONE row; the same loads, the same number of store instructions per byte, half the row visits.
+            const int need2 = min(r + 2, p.ngroups);
+            if (*staged < need2) {
+                int spins = 0;
+                while (*staged < need2) { if (++spins > 8) __nanosleep(SWB_X_WRITERSLEEP); }
+            }
+            asm volatile("" ::: "memory");
+            const int vv = 32 * r + 2 * lane;                          // my two columns of the 64-column window: vv, vv + 1
+            const unsigned long long hcol = hbase + 4ull * (unsigned)vv, pcol = hcol + 4ull * (unsigned long long)pdelta;
+            constexpr int D = 4;
+            int ka[D], kb[D]; unsigned off[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const int2 tb = rowoff[i];
+                off[i] = (unsigned)tb.x;
+                ka[i] = mystage[i * kRowInts + ((vv + tb.y) & (kRowInts - 1))];
+                kb[i] = mystage[i * kRowInts + ((vv + 1 + tb.y) & (kRowInts - 1))];
+            }
+#pragma unroll
+            for (int i = 0; i < kWRows; ++i) {
+                const int xa = ka[i % D], xb = kb[i % D]; const unsigned oo = off[i % D];
+                if (i + D < kWRows) {
+                    const int2 tb = rowoff[i + D];
+                    off[i % D] = (unsigned)tb.x;
+                    ka[i % D] = mystage[(i + D) * kRowInts + ((vv + tb.y) & (kRowInts - 1))];
+                    kb[i % D] = mystage[(i + D) * kRowInts + ((vv + 1 + tb.y) & (kRowInts - 1))];
+                }
+                __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, hcol)), make_int2(xa >> 4, xb >> 4));
+                __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, pcol)), make_int2(xa & 3, xb & 3));
+                if (!SWB_KMAXC) mx = max(mx, max(xa, xb));
+            }
+            __syncwarp();
+            asm volatile("" ::: "memory");
+            if (lane == 0) *drained = r + 2;
+            ++r;
+            continue;
+        }
         const int need = min(r + 1, p.ngroups);
         if (*staged < need) {
             int spins = 0;
@@ -1026,13 +1247,16 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 // loader warp: copies the tagged last row of the band above from global memory (L2)
 // into the first hand-off ring of this band (same slot / epoch tag arithmetic)
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void loader_band(const int4* src, const int nblocks, int4* ring, const int lane,
+// src = entry 0 of the boundary row; entries kFirstEntry .. last are copied.  An entry x may overwrite the ring slot of
+// entry x - kRing once the consumer has used it: at its group start c it has consumed the entries up to c + kInOfs - 1.
+__device__ __forceinline__ void loader_band(const int4* src, const int last, int4* ring, const int lane,
                                             volatile int* consumed)
 {
-    int base = 0;
+    const int nblocks = last + 1;
+    int base = kFirstEntry;
     int idle = 0;
     while (base < nblocks) {
-        const int limit = min(nblocks, *consumed + kRing);
+        const int limit = min(nblocks, *consumed + kRing + kInOfs - 1);
         const int j = base + lane;
         bool ok = false;
         int4 v = make_int4(0, 0, 0, 0);
@@ -1128,7 +1352,7 @@ fill_kernel(const FillParams p_in)
     const long long pair = band_major ? (long long)(s_band % p_in.npairs) : (long long)(s_band / p_in.nbands);
     const int band = band_major ? (int)(s_band / p_in.npairs) : (s_band % p_in.nbands);
     FillParams p = p_in;
-    p.a4 += pair * p.a4_stride;
+    p.a4 += pair * p.a4_stride; p.a4s += pair * p.a4_stride;
     p.b += pair * p.n;
     p.H += pair * p.pair_stride; p.P += pair * p.pair_stride;
     p.boundary += pair * (long long)(p.nbands - 1) * p.bstride;
@@ -1176,7 +1400,7 @@ fill_kernel(const FillParams p_in)
         S.sa = S.sa_base + 16u * (unsigned)lane;                 // slot (t + lane) & (KT-1) at t = 0
         S.ring_in  = (unsigned)__cvta_generic_to_shared(rings + (size_t)w * kRing);
         S.ring_out = (unsigned)__cvta_generic_to_shared(rings + (size_t)(w + 1 < wpc ? w + 1 : w) * kRing);
-        S.jmax = p.jmax;
+        S.jmax = p.in_last;
         S.mcols = (int)p.m;
         {
             const int g16 = p.g_left - kTieLeft;                 // 16 * gap
@@ -1219,7 +1443,9 @@ fill_kernel(const FillParams p_in)
         // block j = t - lane of step t goes to gout[j]: base of the group's first step, the
         // step index is an immediate (only lane 31's copy is ever dereferenced, from t = 31 on)
         S.gout = p.boundary + (size_t)(next_row && (w + 1 == wpc) ? band : 0) * p.bstride + kBoundaryPad - lane;
-        const unsigned* aw = p.a4 + kAPad - lane;                // aw[t] = characters of block t - lane
+        // aw[t] = characters / selectors of my four columns of step t (half skew: odd lanes read the copy that is
+        // shifted by two columns)
+        const unsigned* aw = kHS ? ((lane & 1) ? p.a4s : p.a4) + kAPad - ((lane + 1) >> 1) : p.a4 + kAPad - lane;
         const long long strip = (r0 - 1) / kStripRows;
         compute_strip<KT, STORE, PROF>(p, S, aw, (unsigned)__cvta_generic_to_shared(s_staged + w),
                       (unsigned)__cvta_generic_to_shared(s_drained + w * kWriters),
@@ -1237,7 +1463,7 @@ fill_kernel(const FillParams p_in)
 #pragma unroll
             for (int q = 0; q < kR; ++q) {
                 const long long row = r0 + kR * lane + q;
-                const int col = 4 * (S.rcol[q] - lane) + 3 - (S.rbest[q] & 15);      // step -> block, low bits -> column in it
+                const int col = 4 * S.rcol[q] - kSkewCols * lane + 3 - (S.rbest[q] & 15);      // step -> my columns of it, low bits -> which
                 if (row <= p.n)
                     p.row_best[row] = ((unsigned long long)(unsigned)(S.rbest[q] >> 4) << 32) | (0xffffffffu - (unsigned)col);
                 if (row <= p.n) mx = max(mx, S.rbest[q] >> 4);
@@ -1257,7 +1483,7 @@ fill_kernel(const FillParams p_in)
     } else if (role == 2) {
         // ------------------------------------------------ loader
         if (band == 0 || band_r0 > p.n) return;
-        loader_band(p.boundary + (size_t)(band - 1) * p.bstride + kBoundaryPad, p.jmax + 1, rings, lane, s_consumed);
+        loader_band(p.boundary + (size_t)(band - 1) * p.bstride + kBoundaryPad, p.in_last, rings, lane, s_consumed);
     }
 }
 

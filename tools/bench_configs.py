@@ -23,15 +23,16 @@ def timeit(fn, timer, reps=5):
     return min(ts), sorted(ts)[len(ts) // 2]
 
 
-def single(cols, rows, label, store=True):
+def single(cols, rows, label, store=True, pitch=None):
     a, b = swb.generate(42, cols, rows)
     a_d = torch.frombuffer(bytearray(a), dtype=torch.uint8).to(dev); b_d = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
     timer = swb.KernelTimer(0)
     d_pos = torch.zeros(1, dtype=torch.int64, device=dev); d_sc = torch.zeros(1, dtype=torch.int32, device=dev)
     if store:
-        cells = (rows + 1) * (cols + 1)
+        pitch = pitch or cols + 1
+        cells = (rows + 1) * pitch
         dH = torch.empty(cells, dtype=torch.int32, device=dev); dP = torch.empty(cells, dtype=torch.int32, device=dev)
-        fn = lambda: swb.fill_async(a_d, cols, b_d, rows, dH, dP, cols + 1, d_pos, d_sc, stream=torch.cuda.current_stream(), timer=timer)
+        fn = lambda: swb.fill_async(a_d, cols, b_d, rows, dH, dP, pitch, d_pos, d_sc, stream=torch.cuda.current_stream(), timer=timer)
     else:
         fn = lambda: swb.score_only_async(a_d, cols, b_d, rows, 1, d_pos, d_sc, stream=torch.cuda.current_stream(), timer=timer)
     best, med = timeit(fn, timer)
@@ -69,5 +70,10 @@ for c in args.configs.split(","):
     if c == "batch": batch(256, 256, 65536, "65536 x 256x256 full fill")
     if c == "score": single(45000, 45000, "45000x45000 score only", store=False)
     if c == "score_batch": batch(256, 256, 65536, "65536 x 256x256 score only", store=False)
+    if c == "pitch":
+        for pt in (45001, 45056, 45088, 45312, 46081, 49152, 49153):
+            single(45000, 45000, f"45000x45000 pitch {pt}", pitch=pt)
+        for sz in (28416, 42624, 44928, 56832, 71040):   # 296, 444, 468, 592, 740 strips of 96 rows
+            single(sz, sz, f"{sz}x{sz} ({sz // 96} strips)")
     if c == "big": single(100000, 100000, "100000x100000 full fill (80 GB)")
     torch.cuda.empty_cache()
