@@ -111,10 +111,12 @@ constexpr int kGroup    = 8;           // steps per synchronisation group
 #ifndef SWB_WAIT_STEPS
 #define SWB_WAIT_STEPS 4
 #endif
-constexpr int kWaitSteps = SWB_WAIT_STEPS;   // steps per poll of the strip above (4 or 8); the single-pair full fill uses 8
+constexpr int kWaitSteps = SWB_WAIT_STEPS;   // steps per poll of the strip above (2, 4 or 8); the single-pair full fill uses 8
 #ifndef SWB_WAIT_STEPS_SINGLE
-#define SWB_WAIT_STEPS_SINGLE 8        // measured: 45000x45000 4.99 -> 4.89 ms, 100000x100000 18.7 -> 18.5 ms; the batch and
-#endif                                 // score-only instantiations are 2 % faster with 4
+#define SWB_WAIT_STEPS_SINGLE 8        // measured with the half skew (profiles/r02u_wait_steps.txt), 8 / 4 / 2 steps per poll:
+#endif                                 // 45000x45000 4.29 / 4.32 / 4.48 ms, 100000x100000 17.8 / 17.9 / 18.3 ms, 2 000 000 columns
+                                       // x 1000 rows 52.5 / 58.5 / 65.6 ms; only the chain-bound 1000 x 2 000 000 gains (75.5 / 69.3 /
+                                       // 69.7 ms).  Score-only and batches: 4 beats 2 by 4-10 % and 8 by 2 %.
 // Half skew (SWB_HALF_SKEW, the single-pair geometry): lane l trails lane l-1 by TWO columns instead of four.  A step
 // still covers four columns of each of the lane's rows, but in two halves: the row above the first two columns was
 // produced by the lane above in the second half of ITS previous step, the row above the last two in the first half of
@@ -921,16 +923,20 @@ __device__ __forceinline__ void compute_strip(const FillParams& p, Strip<KT, STO
         // multiple of 8) in the same epoch, block t0+8 is the entry the last step polls anyway
 #define SWB_WAITF(H)                                                                                      \
         if (S.has_in) {                                                                                   \
-            if (kW == 4 && (H) == 0) { while ((lds_volatile_int(in_g + 64u) & 3) != want) { } }  \
-            else                             { while ((lds_volatile_int(in_w) & 3) != want_w) { } }       \
+            if (kW * ((H) + 1) < 8) { while ((lds_volatile_int(in_g + 16u * (unsigned)(kW * ((H) + 1))) & 3) != want) { } }  \
+            else                    { while ((lds_volatile_int(in_w) & 3) != want_w) { } }                \
         }
 #define SWB_STEP(E, I) { if constexpr (kHS) S.template step_hs<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w); \
                          else               S.template step<E, I>(t0 + I, cur[I + 1], in_g, in_w, want, want_w, out_g, out_w, otag, otag_w); }
         // forced = b holds a NUL byte, or column-strip mode (boundary injection): head and tail steps differ.
         // Otherwise a full fill runs the interior step everywhere; score only still masks the columns past m.
-#define SWB_GROUP(M, W) { W(0) SWB_STEP(M, 0); SWB_STEP(M, 1); SWB_STEP(M, 2); SWB_STEP(M, 3);       \
-                          if (kW == 4) { W(1) }                                               \
-                          SWB_STEP(M, 4); SWB_STEP(M, 5); SWB_STEP(M, 6); SWB_STEP(M, 7); }
+#define SWB_GROUP(M, W) { W(0) SWB_STEP(M, 0); SWB_STEP(M, 1);                                        \
+                          if (kW == 2) { W(1) }                                               \
+                          SWB_STEP(M, 2); SWB_STEP(M, 3);                                     \
+                          if (kW == 4) { W(1) } else if (kW == 2) { W(2) }                    \
+                          SWB_STEP(M, 4); SWB_STEP(M, 5);                                     \
+                          if (kW == 2) { W(3) }                                               \
+                          SWB_STEP(M, 6); SWB_STEP(M, 7); }
         // (only in the single-pair full-fill instantiation: the others are compiled for two CTAs per SM and have no
         // registers to spare for a fifth copy of the group)
         if ((KT == 64 && STORE) && g <= gtail && !(forced && g < 4)) SWB_GROUP(0, SWB_WAITF)
@@ -1019,55 +1025,10 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
 #ifdef SWB_X_WRITERTRACE
     long long dw_wait = 0, dw_work = 0, dw_n = 0;
 #endif
-#ifndef SWB_WRITER_WIDE
-#define SWB_WRITER_WIDE 0              // 1: interior rounds are flushed two at a time: 64 columns = 256 contiguous bytes per row visit
-#endif
     for (int r = 0; r < rounds; ++r) {
 #ifdef SWB_X_WRITERTRACE
         const long long wc0 = clock64();
 #endif
-        if (SWB_WRITER_WIDE && KT == 64 && (r & 1) == 0 && r + 1 < rounds && nvalid == kWRows &&
-            (32 * r - Emax >= (p.left_in != nullptr ? 1 : 0)) && (32 * (r + 1) + 31 - Emin <= m - (p.right_out != nullptr ? 1 : 0))) {
-            // Two interior rounds at once.  The store pattern, not the instruction count, bounds the writers: a row
-            // visit of one 128-byte line per matrix opens a DRAM page for 128 bytes (tools/ubench_pattern.cu: 4.4 TB/s,
-            // 5.2 TB/s with two lines per visit).  One warp-wide 8-byte store covers the 64 columns = two adjacent lines
-            // of ONE row; the same loads, the same number of store instructions per byte, half the row visits.
-            const int need2 = min(r + 2, p.ngroups);
-            if (*staged < need2) {
-                int spins = 0;
-                while (*staged < need2) { if (++spins > 8) __nanosleep(SWB_X_WRITERSLEEP); }
-            }
-            asm volatile("" ::: "memory");
-            const int vv = 32 * r + 2 * lane;                          // my two columns of the 64-column window: vv, vv + 1
-            const unsigned long long hcol = hbase + 4ull * (unsigned)vv, pcol = hcol + 4ull * (unsigned long long)pdelta;
-            constexpr int D = 4;
-            int ka[D], kb[D]; unsigned off[D];
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                const int2 tb = rowoff[i];
-                off[i] = (unsigned)tb.x;
-                ka[i] = mystage[i * kRowInts + ((vv + tb.y) & (kRowInts - 1))];
-                kb[i] = mystage[i * kRowInts + ((vv + 1 + tb.y) & (kRowInts - 1))];
-            }
-#pragma unroll
-            for (int i = 0; i < kWRows; ++i) {
-                const int xa = ka[i % D], xb = kb[i % D]; const unsigned oo = off[i % D];
-                if (i + D < kWRows) {
-                    const int2 tb = rowoff[i + D];
-                    off[i % D] = (unsigned)tb.x;
-                    ka[i % D] = mystage[(i + D) * kRowInts + ((vv + tb.y) & (kRowInts - 1))];
-                    kb[i % D] = mystage[(i + D) * kRowInts + ((vv + 1 + tb.y) & (kRowInts - 1))];
-                }
-                __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, hcol)), make_int2(xa >> 4, xb >> 4));
-                __stcs(reinterpret_cast<int2*>(mad_wide(oo, one, pcol)), make_int2(xa & 3, xb & 3));
-                if (!SWB_KMAXC) mx = max(mx, max(xa, xb));
-            }
-            __syncwarp();
-            asm volatile("" ::: "memory");
-            if (lane == 0) *drained = r + 2;
-            ++r;
-            continue;
-        }
         const int need = min(r + 1, p.ngroups);
         if (*staged < need) {
             int spins = 0;

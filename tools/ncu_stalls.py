@@ -5,7 +5,8 @@ rep = sys.argv[1]; N = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
+he = next((i for i in range(hi + 1, len(rows)) if rows[i] and rows[i][0] == "Kernel Name"), len(rows))   # first kernel only
+hdr, data = rows[hi], [r for r in rows[hi + 1:he] if len(r) == len(rows[hi])]
 iS, isrc, iex = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
 stall = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 tot = sum(int(r[iS] or 0) for r in data)
