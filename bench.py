@@ -21,9 +21,12 @@ value  = cols*rows / max-over-ranks(step time) / 1e9 with the sequences already 
          timed steps run as a pipeline over two H/P buffer sets: the backtrack of step k (a serial
          pointer chase that occupies one SM) overlaps the fill of step k+1 on a second stream; nothing
          is skipped.  `serial` repeats the measurement one step at a time (the latency of a step).
-         At N>1 the steps run one at a time (the all-gather of maxPos separates consecutive fills);
+         At N>1 the same pipeline runs over two sets of strip buffers per GPU;
 e2e    = the same metric through the host-buffer C-ABI call (swb_ctx_align): H2D of a and
-         b, fill, backtrack and the D2H of H, P (16.2 GB, pinned) inside the timed region;
+         b, fill, backtrack and the delivery of int32 H and P (16.2 GB) into the caller's pinned host
+         buffers inside the timed region.  The library moves one byte per cell over PCIe (row step of
+         H + P, swb_pack.cu) and expands it on the host threads; the host buffers are checked against
+         the oracle's digests after the timed steps (`e2e.parity`);
 roofline = the fill kernel alone: 8 B/cell x (rows+1)(cols+1) cells / its CUDA-event time,
          against MEASURED_PEAKS.json's HBM figure;
 cpu_baseline = the unmodified reference (oracle/_ref, built from /root/reference by
@@ -347,11 +350,14 @@ def secondary_single_gpu(swb, torch, dev, local, peak):
         dH = torch.empty(cells, dtype=torch.int32, device=dev); dP = torch.empty(cells, dtype=torch.int32, device=dev)
         ms = best_of(lambda: swb.fill_async(a_d, c, b_d, r, dH, dP, c + 1, d_pos, d_sc, device=local, stream=stream, timer=timer))
         nstrips = (r + 95) // 96                             # single pairs: strips of 96 rows (32 lanes x 3 rows)
-        steps_chain = nstrips * 40 + (c // 4 + 32)           # strips x (32 lanes + poll granularity) + one strip's sweep
+        # strips x (steps lane 31 trails lane 0 + poll granularity) + one strip's sweep.  Half skew (lane l trails
+        # lane l-1 by two columns) unless the pair is more than three times wider than tall (swb_api.cu: fill_impl)
+        skew = 32 if c > 3 * r else 16
+        steps_chain = nstrips * (skew + 8) + (c // 4 + skew)
         out[f"skewed_{c}x{r}"] = {"workload": f"{c} cols x {r} rows full fill", "kernel_ms": ms, "gcups": c * r / ms / 1e6,
                                   "hbm_frac": 8.0 * cells / ms / 1e6 / peak, "maxPos": int(d_pos.item()),
                                   "latency_bound": {"chain_steps": steps_chain, "t_step_ns": ms * 1e6 / steps_chain,
-                                                    "what": "strips*(32+8) + cols/4+32 dependent steps (96-row strips); t_step = kernel time / chain steps "
+                                                    "what": f"strips*({skew}+8) + cols/4+{skew} dependent steps (96-row strips, {'full' if skew == 32 else 'half'} skew); t_step = kernel time / chain steps "
                                                             "(the in-situ cost of one 3x4-cell step when the chain is the only limiter)"}}
         del dH, dP
     # batch: 65536 x 256x256 in one launch (BASELINE configs[4]); sharded pair-wise when N > 1
@@ -504,7 +510,7 @@ def run_single(args, torch, swb, dev, local):
         except (ValueError, OSError):
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_source, "kernel": "swb_tall::fill_kernel<64,true,true> (96-row strips, score look-up)",
+                "traffic": traffic, "traffic_source": traffic_source, "kernel": "swb_tall::fill_kernel<64,true,true> (96-row strips, half skew, score look-up)",
                 "kernel_ms_avg": fill_avg, "kernel_ms_min": min(fill_ms_serial), "kernel_ms_avg_in_pipelined_region": statistics.mean(fill_ms),
                 "timed_in": "the K one-at-a-time timed steps (`serial`), CUDA events around the launch on its stream",
                 "algorithmic_bytes_per_launch": 8 * cells_padded,

@@ -43,8 +43,9 @@ def main():
         def to_bytes(key):
             u = units[hdr.index(key)].lower(); v = float(d[key].replace(",", ""))
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}[u]
-        traffic = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-        lines.append(f"   dram traffic per launch (read+write)                                         {traffic:16.0f} byte")
+        t = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+        traffic = max(traffic or 0.0, t)          # (the instantiation that does not apply returns at once: take the one that ran)
+        lines.append(f"   dram traffic per launch (read+write)                                         {t:16.0f} byte")
     open(args.out, "w").write("\n".join(lines) + "\n")
     if args.traffic_json and traffic is not None:
         json.dump({"cols": args.cols, "rows": args.rows, "dram_bytes_per_launch": traffic, "source": args.out},
