@@ -830,13 +830,34 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
             a_host = torch.frombuffer(bytearray(a[s2.col0:s2.col0 + s2.m]), dtype=torch.uint8).pin_memory()
             b_host = torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
 
+            # packed transfer of the strip (swb_pack.cu): columns 1..m_local as one byte per cell + a row base, expanded
+            # into the pinned int32 buffers by this rank's share of the host cores; local column 0 (the copy of the
+            # left neighbour's last column, P = hand-off marker) goes as it is
+            packed = os.environ.get("SWB_PACKED_D2H", "") != "0"
+            # host threads per rank: the cores this rank is bound to, shared with the ranks bound to the same set
+            mine = tuple(sorted(os.sched_getaffinity(0))) if hasattr(os, "sched_getaffinity") else tuple(range(os.cpu_count() or 1))
+            sets = [None] * world
+            dist.all_gather_object(sets, mine)
+            threads = max(1, len(mine) // max(1, sum(1 for x in sets if x == mine)))
+            if packed:
+                nscr = swb.d2h_packed_scratch_bytes(rows + 1, s2.m)
+                d_scr = torch.empty(nscr, dtype=torch.uint8, device=dev); h_scr = torch.empty(nscr, dtype=torch.uint8).pin_memory()
+            hHv, hPv = hH.view(rows + 1, s2.pitch), hP.view(rows + 1, s2.pitch)
+            dHv, dPv = s2.dH.view(rows + 1, s2.pitch), s2.dP.view(rows + 1, s2.pitch)
+
             def estep():
                 s2.a_d.copy_(a_host, non_blocking=True); s2.b_d.copy_(b_host, non_blocking=True)
                 pipe2.fill_async(stream=stream)
-                hH.copy_(s2.dH, non_blocking=True)             # H is final after the fill
+                if not packed:
+                    hH.copy_(s2.dH, non_blocking=True)         # H is final after the fill
                 mp = pipe2.maxpos()
                 pl = pipe2.backtrack(mp)
-                hP.copy_(s2.dP, non_blocking=True)
+                if packed:
+                    hHv[:, 0].copy_(dHv[:, 0]); hPv[:, 0].copy_(dPv[:, 0])
+                    swb.d2h_packed(s2.dH[1:], s2.dP[1:], s2.pitch, rows + 1, s2.m, hH[1:], hP[1:], s2.pitch, d_scr, h_scr,
+                                   threads=threads, device=local, stream=stream)
+                else:
+                    hP.copy_(s2.dP, non_blocking=True)
                 torch.cuda.synchronize()
                 return mp, pl
             estep(); barrier()
@@ -849,11 +870,29 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
             te = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
             dt = float(te.item())
+            # what the caller received in HOST memory against the oracle's digests (uploaded again for the arithmetic)
+            e2e_parity = None
+            if g is not None:
+                cH = hH.to(dev).view(rows + 1, s2.pitch); cP = hP.to(dev).view(rows + 1, s2.pitch)
+                checked, bad = check_digests(g, cH, cP.abs(), s2.col0, s2.m)
+                ok = bool((cH == dHv).all().item() and (cP == dPv).all().item())     # incl. local column 0 and the path marks
+                tp = torch.tensor([checked, bad, 0 if ok else 1], dtype=torch.int64, device=dev)
+                dist.all_reduce(tp)
+                e2e_parity = {"digests_checked": int(tp[0].item()), "digest_mismatches": int(tp[1].item()),
+                              "host_equals_device_on_every_rank": int(tp[2].item()) == 0}
+                del cH, cP
+            d2h_all = torch.tensor([(swb.packed_pitch(s2.m) * (rows + 1) + 12 * (rows + 1) + 24) if packed else (8 * (rows + 1) * s2.pitch + 24)],
+                                   dtype=torch.int64, device=dev)
+            dist.all_reduce(d2h_all)
             e2e = {"value": cols * rows / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": cols + rows * world,
-                   "d2h_bytes_per_step": 8 * (rows + 1) * (cols + world) + 24 * world, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+                   "d2h_bytes_per_step": int(d2h_all.item()), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+                   "host_bytes_delivered_per_step": 8 * (rows + 1) * (cols + world) + 24 * world,
+                   "transfer": (f"packed: one byte per cell over PCIe, expanded into each rank's pinned int32 strip by {threads} host threads per rank"
+                                if packed else "plain int32 copies"),
+                   "parity": e2e_parity,
                    "host_placement": numa,
-                   "api": "StripPipeline (swb_fill_strip_async / swb_backtrack_from_async per rank): host a, b -> each rank's strip of "
-                          "H and P (after backtrack) in pinned host memory, maxPos, path length"}
+                   "api": "StripPipeline (swb_fill_strip_async / swb_backtrack_from_async per rank, swb_d2h_packed): host a, b -> each rank's "
+                          "strip of int32 H and P (after backtrack) in pinned host memory, maxPos, path length"}
             pipe2.close()
         except Exception as e:
             e2e = {"error": repr(e)[:300]}

@@ -58,10 +58,10 @@ typedef struct { int32_t match, mismatch, gap; } swb_scoring;
 /* Tuning knobs (0 = library default).  Not part of the reference surface. */
 typedef struct swb_timer swb_timer;   /* CUDA-event pair around the fill kernel only */
 typedef struct {
-    int32_t warps_per_band;   /* compute warps (64-row strips) per CTA band, 1..2 (larger values are clamped to 2) */
+    int32_t warps_per_band;   /* compute warps (strips: 96 rows for a single pair, 64 rows in a batch) per CTA band, 1..2 (larger values are clamped to 2) */
     int32_t reserved[5];
     swb_timer* timer;         /* if set, swb_fill_async brackets the fill kernel launch with its events */
-    uint64_t* trace;          /* developer tool: DEVICE buffer of ceil(n/64)*8 uint64 globaltimer stamps (8 per 64-row strip), or NULL; honoured by the -DSWB_TRACE developer build only */
+    uint64_t* trace;          /* developer tool: DEVICE buffer of ceil(n/64)*8 uint64 globaltimer stamps (8 per strip; strips are 96 rows for a single pair, 64 in a batch), or NULL; honoured by the -DSWB_TRACE developer build only */
 } swb_tuning;
 
 /* Kernel-only timing for the roofline figure: events are recorded on the call's stream
@@ -128,23 +128,36 @@ void swb_ctx_destroy(swb_ctx* ctx);
  * duration of the fill.  On the wire one byte per cell is enough: bits 7..3 = H[i][j] - H[i][j-1] + 16
  * (the recurrence bounds the row step of H by gap .. match - gap, omp_smithW.c:331-388), bits 2..0 =
  * P[i][j] + 3 (directions 0..3, negated on the path, omp_smithW.c:405-420).
- *   swb_pack_rows_async  DEVICE: rows row0 .. row0+nrows-1, columns 0 .. cols-1 of dH/dP (row pitch `pitch`,
- *                        column -1 counts as 0) -> d_packed (row pitch packed_pitch >= cols, a multiple of 4;
- *                        swb_packed_pitch(cols) gives the canonical one).  *d_overflow (device int, zeroed by
- *                        the caller) is set to 1 when a value does not fit; the packed bytes are then
- *                        meaningless and the caller must copy the int32 matrices instead.
- *   swb_expand_rows      HOST: packed rows -> int32 H and/or P (either may be NULL), bit-exact, on `threads`
- *                        host threads (0 = swb_host_threads(): SWB_HOST_THREADS or the hardware concurrency).
- * swb_ctx_align uses the pair for matrices of 32 MiB and more (SWB_PACKED_D2H=0 turns that off, =1 forces it):
- * the packed bytes are copied in chunks and expanded while later chunks are in flight; the caller still receives
- * the reference's int32 matrices.  A caller that only needs parts of H/P (say the rows a path crosses) can keep the
- * packed form and expand just those rows. */
+ *   swb_pack_rows_async  DEVICE: rows row0 .. row0+nrows-1, columns 0 .. cols-1 of dH/dP (row pitch `pitch`) ->
+ *                        d_packed (row pitch packed_pitch >= cols, a multiple of 4; swb_packed_pitch(cols) gives
+ *                        the canonical one).  d_row_base == NULL: column -1 counts as 0 (a whole matrix: column 0
+ *                        is 0).  d_row_base != NULL (DEVICE, nrows int32): receives H of column 0 of every row and
+ *                        column 0's step is stored as 0 -- for sub-matrices whose first column is not 0 (a column
+ *                        strip: pass dH + c0, dP + c0).  *d_overflow (device int, zeroed by the caller) is set to 1
+ *                        when a value does not fit; the packed bytes are then meaningless and the caller must copy
+ *                        the int32 matrices instead.
+ *   swb_expand_rows      HOST: packed rows -> int32 H and/or P (either may be NULL), bit-exact, starting every row
+ *                        from row_base[r] (NULL: 0), on `threads` host threads (0 = swb_host_threads():
+ *                        SWB_HOST_THREADS, else the cores this process may run on).
+ *   swb_d2h_packed       both halves for a whole (sub-)matrix: packs rows 0..nrows-1 x columns 0..cols-1 of dH/dP,
+ *                        copies the bytes in chunks and expands them into HOST H / P (row pitch host_pitch; either
+ *                        may be NULL) while later chunks are in flight; falls back to plain copies when the flag
+ *                        is raised.  Synchronous (returns when H and P are complete).  d_scratch (device) and
+ *                        h_scratch (pinned host) hold swb_d2h_packed_scratch_bytes(nrows, cols) bytes each.
+ * swb_ctx_align uses it for matrices of 32 MiB and more (SWB_PACKED_D2H=0 turns that off, =1 forces it); the caller
+ * still receives the reference's int32 matrices.  A caller that only needs parts of H/P (say the rows a path
+ * crosses) can keep the packed form and expand just those rows. */
 int64_t swb_packed_pitch(int64_t cols);
 int  swb_host_threads(void);
 int  swb_pack_rows_async(const int32_t* dH, const int32_t* dP, int64_t pitch, int64_t row0, int64_t nrows, int64_t cols,
-                         unsigned char* d_packed, int64_t packed_pitch, int* d_overflow, int device, void* stream);
+                         unsigned char* d_packed, int64_t packed_pitch, int* d_overflow, int32_t* d_row_base, int device,
+                         void* stream);
 int  swb_expand_rows(const unsigned char* packed, int64_t packed_pitch, int64_t nrows, int64_t cols,
-                     int32_t* H, int32_t* P, int64_t pitch, int threads);
+                     int32_t* H, int32_t* P, int64_t pitch, const int32_t* row_base, int threads);
+size_t swb_d2h_packed_scratch_bytes(int64_t nrows, int64_t cols);
+int  swb_d2h_packed(const int32_t* dH, const int32_t* dP, int64_t pitch, int64_t nrows, int64_t cols,
+                    int32_t* H, int32_t* P, int64_t host_pitch, void* d_scratch, void* h_scratch, int threads, int device,
+                    void* stream);
 
 /* Score-only variant (no H/P stores): max score and maxPos with the reference
  * tie-break.  Replaces the -DSKIP_BACKTRACK style runs of the reference's

@@ -114,8 +114,10 @@ def _load() -> C.CDLL:
     L.swb_traceback_async.restype = C.c_int; L.swb_alignment_from_moves.restype = C.c_int
     L.swb_packed_pitch.argtypes = [i64]; L.swb_packed_pitch.restype = i64
     L.swb_host_threads.argtypes = []; L.swb_host_threads.restype = C.c_int
-    L.swb_pack_rows_async.argtypes = [vp, vp, i64, i64, i64, i64, vp, i64, vp, C.c_int, vp]; L.swb_pack_rows_async.restype = C.c_int
-    L.swb_expand_rows.argtypes = [vp, i64, i64, i64, vp, vp, i64, C.c_int]; L.swb_expand_rows.restype = C.c_int
+    L.swb_pack_rows_async.argtypes = [vp, vp, i64, i64, i64, i64, vp, i64, vp, vp, C.c_int, vp]; L.swb_pack_rows_async.restype = C.c_int
+    L.swb_expand_rows.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp, C.c_int]; L.swb_expand_rows.restype = C.c_int
+    L.swb_d2h_packed_scratch_bytes.argtypes = [i64, i64]; L.swb_d2h_packed_scratch_bytes.restype = C.c_size_t
+    L.swb_d2h_packed.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, vp, vp, C.c_int, C.c_int, vp]; L.swb_d2h_packed.restype = C.c_int
     for name in ("swb_fill_pairs_async", "swb_shard_pairs", "swb_multi_create", "swb_multi_fill", "swb_multi_backtrack",
                  "swb_multi_align", "swb_multi_strips", "swb_multi_strip", "swb_multi_gather_host", "swb_fill_multi",
                  "swb_seq_count", "swb_seq_read", "swb_manifest_load", "swb_manifest_pair"):
@@ -452,15 +454,26 @@ def host_threads() -> int:
 
 
 def pack_rows_async(dH, dP, pitch: int, row0: int, nrows: int, cols: int, d_packed, packed_pitch_: int, d_overflow,
-                    device: int = 0, stream=None) -> None:
+                    d_row_base=None, device: int = 0, stream=None) -> None:
     """DEVICE: one byte per cell (row step of H + P) of rows row0 .. row0+nrows-1 (include/swb200.h, packed transfer)."""
     _check(lib.swb_pack_rows_async(_ptr(dH), _ptr(dP), pitch, row0, nrows, cols, _ptr(d_packed), packed_pitch_,
-                                   _ptr(d_overflow), device, _stream_ptr(stream)))
+                                   _ptr(d_overflow), _ptr(d_row_base), device, _stream_ptr(stream)))
 
 
-def expand_rows(packed, packed_pitch_: int, nrows: int, cols: int, H, P, pitch: int, threads: int = 0) -> None:
+def expand_rows(packed, packed_pitch_: int, nrows: int, cols: int, H, P, pitch: int, row_base=None, threads: int = 0) -> None:
     """HOST: packed rows -> int32 H and/or P (bit-exact)."""
-    _check(lib.swb_expand_rows(_ptr(packed), packed_pitch_, nrows, cols, _ptr(H), _ptr(P), pitch, threads))
+    _check(lib.swb_expand_rows(_ptr(packed), packed_pitch_, nrows, cols, _ptr(H), _ptr(P), pitch, _ptr(row_base), threads))
+
+
+def d2h_packed_scratch_bytes(nrows: int, cols: int) -> int:
+    return int(lib.swb_d2h_packed_scratch_bytes(nrows, cols))
+
+
+def d2h_packed(dH, dP, pitch: int, nrows: int, cols: int, H, P, host_pitch: int, d_scratch, h_scratch, threads: int = 0,
+               device: int = 0, stream=None) -> None:
+    """Device H/P -> HOST int32 H/P through the packed transfer (synchronous; plain copies if the format does not fit)."""
+    _check(lib.swb_d2h_packed(_ptr(dH), _ptr(dP), pitch, nrows, cols, _ptr(H), _ptr(P), host_pitch, _ptr(d_scratch),
+                              _ptr(h_scratch), threads, device, _stream_ptr(stream)))
 
 
 def cigar_from_moves(moves: bytes) -> str:

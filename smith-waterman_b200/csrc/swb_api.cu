@@ -127,12 +127,6 @@ struct StripLink {                         // column-strip mode (nullptr members
 
 }  // namespace
 
-// swb_pack.cu: chunked copy of packed rows with the host-side expansion running beside it
-namespace swb_packed {
-int copy_and_expand(const unsigned char* d_packed, unsigned char* h_packed, long long packed_pitch, long long nrows, long long cols,
-                    int32_t* H, int32_t* P, long long pitch, cudaStream_t st, int device, int threads, int nchunks);
-}
-
 // The fill's host side, once per kernel geometry (see swb_fill_impl.inc)
 namespace swb {
 #include "swb_fill_impl.inc"
@@ -511,7 +505,7 @@ struct swb_ctx {
     int32_t* dH = nullptr; int32_t* dP = nullptr;
     long long* d_scalars = nullptr;        // [0] maxPos, [1] pathLen, [2] packed-transfer overflow flag
     cudaStream_t st = nullptr;
-    // packed copy-back (swb_pack.cu): one byte per cell on the device and in pinned host memory, allocated on first use
+    // packed copy-back (swb_pack.cu): scratch for swb_d2h_packed on the device and in pinned host memory, allocated on first use
     unsigned char* d_packed = nullptr; unsigned char* h_packed = nullptr;
     bool packed_tried = false;
 };
@@ -567,12 +561,11 @@ int swb_ctx_align(swb_ctx* c, const char* a, const char* b, const swb_scoring* s
     DeviceGuard guard(c->device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
     const size_t bytes = (size_t)(c->m + 1) * (size_t)(c->n + 1) * sizeof(int32_t);
-    const int64_t ppitch = swb_packed_pitch(c->m + 1);
     bool packed = (H || P) && packed_wanted(bytes);
     if (packed && !c->packed_tried) {
         // (a context whose packed buffers cannot be had keeps working with the plain copies)
         c->packed_tried = true;
-        const size_t pbytes = (size_t)ppitch * (size_t)(c->n + 1);
+        const size_t pbytes = swb_d2h_packed_scratch_bytes(c->n + 1, c->m + 1);
         if (cudaMalloc(reinterpret_cast<void**>(&c->d_packed), pbytes) != cudaSuccess) { c->d_packed = nullptr; cudaGetLastError(); }
         else if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_packed), pbytes, cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError(); cudaFree(c->d_packed); c->d_packed = nullptr; c->h_packed = nullptr;
@@ -592,27 +585,13 @@ int swb_ctx_align(swb_ctx* c, const char* a, const char* b, const swb_scoring* s
         SWB_CUDA(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(long long), c->st));
     }
     long long sc3[3] = {0, 0, 0};
+    SWB_CUDA(cudaMemcpyAsync(sc3, c->d_scalars, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
     if (packed) {
         // one byte per cell over PCIe, expanded into the caller's int32 matrices on the host (swb_pack.cu)
-        SWB_CUDA(cudaMemsetAsync(c->d_scalars + 2, 0, sizeof(long long), c->st));
-        rc = swb_pack_rows_async(c->dH, c->dP, c->m + 1, 0, c->n + 1, c->m + 1, c->d_packed, ppitch,
-                                 reinterpret_cast<int*>(c->d_scalars + 2), c->device, c->st);
-        if (rc != SWB_OK) return rc;
-        SWB_CUDA(cudaMemcpyAsync(sc3, c->d_scalars, sizeof sc3, cudaMemcpyDeviceToHost, c->st));
-        SWB_CUDA(cudaStreamSynchronize(c->st));
-        if (sc3[2] == 0) {
-            rc = swb_packed::copy_and_expand(c->d_packed, c->h_packed, ppitch, c->n + 1, c->m + 1, H, P, c->m + 1, c->st,
-                                             c->device, 0, 24);
-            if (rc != SWB_OK) return rc;
-        } else {
-            // some row step of H or some P value does not fit the byte format (exotic scoring): plain copies
-            if (H) SWB_CUDA(cudaMemcpyAsync(H, c->dH, bytes, cudaMemcpyDeviceToHost, c->st));
-            if (P) SWB_CUDA(cudaMemcpyAsync(P, c->dP, bytes, cudaMemcpyDeviceToHost, c->st));
-            SWB_CUDA(cudaStreamSynchronize(c->st));
-        }
+        rc = swb_d2h_packed(c->dH, c->dP, c->m + 1, c->n + 1, c->m + 1, H, P, c->m + 1, c->d_packed, c->h_packed, 0, c->device, c->st);
+        if (rc != SWB_OK) return rc == SWB_ERR_CUDA ? cuda_fail(cudaGetLastError(), "swb_d2h_packed", __LINE__) : rc;
     } else {
         if (P) SWB_CUDA(cudaMemcpyAsync(P, c->dP, bytes, cudaMemcpyDeviceToHost, c->st));
-        SWB_CUDA(cudaMemcpyAsync(sc3, c->d_scalars, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
         SWB_CUDA(cudaStreamSynchronize(c->st));
     }
     if (maxPos) *maxPos = sc3[0];

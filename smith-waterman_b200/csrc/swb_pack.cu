@@ -20,6 +20,9 @@
 #include <cstdlib>
 #include <thread>
 #include <vector>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -31,7 +34,8 @@ constexpr int kDeltaBias = 16, kPBias = 3;
 // one block per row; thread t packs cells t, t+256, ...; four neighbouring lanes merge their bytes into one 32-bit store
 __global__ void __launch_bounds__(256) pack_rows_kernel(const int32_t* __restrict__ H, const int32_t* __restrict__ P, long long pitch,
                                                         long long row0, long long cols, unsigned char* __restrict__ out,
-                                                        long long out_pitch, int* __restrict__ overflow)
+                                                        long long out_pitch, int* __restrict__ overflow,
+                                                        int32_t* __restrict__ row_base)
 {
     const long long r = blockIdx.x;
     const int32_t* h = H + (row0 + r) * pitch;
@@ -44,7 +48,9 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const int32_t* __restric
         int hv = 0, pv = 0;
         if (j < cols) { hv = __ldcs(h + j); pv = __ldcs(q + j); }
         int prev = __shfl_up_sync(0xffffffffu, hv, 1);
-        if (lane == 0) prev = (j > 0 && j < cols) ? __ldg(h + j - 1) : 0;
+        // column 0: its step counts from 0, or -- with a row base -- from itself (the base carries the value)
+        if (lane == 0) prev = (j > 0 && j < cols) ? __ldg(h + j - 1) : (row_base != nullptr ? hv : 0);
+        if (j == 0 && row_base != nullptr) row_base[r] = hv;
         const int d = hv - prev + kDeltaBias, pp = pv + kPBias;
         if (j < cols && (((unsigned)d > 31u) | ((unsigned)pp > 6u))) bad = true;
         unsigned w = j < cols ? ((((unsigned)d & 31u) << 3) | ((unsigned)pp & 7u)) << (8 * (lane & 3)) : 0u;
@@ -56,9 +62,8 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const int32_t* __restric
 }
 
 // ---- host side: one row of packed bytes -> int32 H and P
-void expand_row_scalar(const unsigned char* src, long long cols, int32_t* h, int32_t* p)
+void expand_row_scalar(const unsigned char* src, long long cols, int32_t* h, int32_t* p, int acc)
 {
-    int acc = 0;
     if (h && p) for (long long j = 0; j < cols; ++j) { const int v = src[j]; acc += (v >> 3) - kDeltaBias; h[j] = acc; p[j] = (v & 7) - kPBias; }
     else if (h) for (long long j = 0; j < cols; ++j) { acc += (src[j] >> 3) - kDeltaBias; h[j] = acc; }
     else if (p) for (long long j = 0; j < cols; ++j) p[j] = (src[j] & 7) - kPBias;
@@ -67,10 +72,9 @@ void expand_row_scalar(const unsigned char* src, long long cols, int32_t* h, int
 #if defined(__x86_64__)
 // eight cells per iteration; non-temporal stores (the matrices are several times the last-level cache, a normal store
 // would read every line before overwriting it)
-__attribute__((target("avx2"))) void expand_row_avx2(const unsigned char* src, long long cols, int32_t* h, int32_t* p)
+__attribute__((target("avx2"))) void expand_row_avx2(const unsigned char* src, long long cols, int32_t* h, int32_t* p, int acc)
 {
     long long j = 0;
-    int acc = 0;
     // scalar head until the output pointers are 32-byte aligned (H and P share the row offset; when their bases
     // differ mod 32 only one of them can be aligned: that one streams, the other uses unaligned stores)
     int32_t* lead = h ? h : p;
@@ -112,16 +116,17 @@ __attribute__((target("avx2"))) void expand_row_avx2(const unsigned char* src, l
 #endif
 
 void expand_rows_range(const unsigned char* packed, long long packed_pitch, long long r_lo, long long r_hi, long long cols,
-                       int32_t* H, int32_t* P, long long pitch, bool avx2)
+                       int32_t* H, int32_t* P, long long pitch, bool avx2, const int32_t* row_base)
 {
     for (long long r = r_lo; r < r_hi; ++r) {
         const unsigned char* src = packed + r * packed_pitch;
         int32_t* h = H ? H + r * pitch : nullptr;
         int32_t* p = P ? P + r * pitch : nullptr;
+        const int acc = row_base ? row_base[r] : 0;
 #if defined(__x86_64__)
-        if (avx2) { expand_row_avx2(src, cols, h, p); continue; }
+        if (avx2) { expand_row_avx2(src, cols, h, p, acc); continue; }
 #endif
-        expand_row_scalar(src, cols, h, p);
+        expand_row_scalar(src, cols, h, p, acc);
     }
 #if defined(__x86_64__)
     if (avx2) _mm_sfence();
@@ -144,14 +149,20 @@ extern "C" {
 int swb_host_threads(void)
 {
     if (const char* s = std::getenv("SWB_HOST_THREADS")) { const int v = std::atoi(s); if (v > 0) return std::min(v, 256); }
-    const unsigned hc = std::thread::hardware_concurrency();
+    unsigned hc = std::thread::hardware_concurrency();
+#if defined(__linux__)
+    // the cores this process may run on (a rank pinned to its GPU's NUMA node must not count the other node's)
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) { const int c = CPU_COUNT(&set); if (c > 0) hc = (unsigned)c; }
+#endif
     return (int)std::min(64u, std::max(1u, hc));
 }
 
 int64_t swb_packed_pitch(int64_t cols) { return (cols + 63) & ~(int64_t)63; }
 
 int swb_pack_rows_async(const int32_t* dH, const int32_t* dP, int64_t pitch, int64_t row0, int64_t nrows, int64_t cols,
-                        unsigned char* d_packed, int64_t packed_pitch, int* d_overflow, int device, void* stream)
+                        unsigned char* d_packed, int64_t packed_pitch, int* d_overflow, int32_t* d_row_base, int device,
+                        void* stream)
 {
     if (!dH || !dP || !d_packed || !d_overflow || nrows < 0 || cols <= 0 || pitch < cols || packed_pitch < cols ||
         (packed_pitch & 3) != 0 || row0 < 0)
@@ -164,25 +175,25 @@ int swb_pack_rows_async(const int32_t* dH, const int32_t* dP, int64_t pitch, int
     int rc = SWB_OK;
     // (grid.x carries the rows: up to 2^31-1)
     pack_rows_kernel<<<(unsigned)nrows, 256, 0, static_cast<cudaStream_t>(stream)>>>(dH, dP, pitch, row0, cols, d_packed, packed_pitch,
-                                                                                   d_overflow);
+                                                                                   d_overflow, d_row_base);
     if (cudaGetLastError() != cudaSuccess) rc = SWB_ERR_CUDA;
     if (cur != device) cudaSetDevice(cur);
     return rc;
 }
 
 int swb_expand_rows(const unsigned char* packed, int64_t packed_pitch, int64_t nrows, int64_t cols,
-                    int32_t* H, int32_t* P, int64_t pitch, int threads)
+                    int32_t* H, int32_t* P, int64_t pitch, const int32_t* row_base, int threads)
 {
     if (!packed || nrows < 0 || cols <= 0 || packed_pitch < cols || pitch < cols) return SWB_ERR_ARG;
     if (!H && !P) return SWB_OK;
     if (threads <= 0) threads = swb_host_threads();
     threads = (int)std::min<int64_t>(threads, std::max<int64_t>(1, nrows));
     const bool avx2 = have_avx2();
-    if (threads == 1) { expand_rows_range(packed, packed_pitch, 0, nrows, cols, H, P, pitch, avx2); return SWB_OK; }
+    if (threads == 1) { expand_rows_range(packed, packed_pitch, 0, nrows, cols, H, P, pitch, avx2, row_base); return SWB_OK; }
     std::vector<std::thread> pool;
     pool.reserve(threads);
     for (int t = 0; t < threads; ++t)
-        pool.emplace_back([=] { expand_rows_range(packed, packed_pitch, nrows * t / threads, nrows * (t + 1) / threads, cols, H, P, pitch, avx2); });
+        pool.emplace_back([=] { expand_rows_range(packed, packed_pitch, nrows * t / threads, nrows * (t + 1) / threads, cols, H, P, pitch, avx2, row_base); });
     for (auto& th : pool) th.join();
     return SWB_OK;
 }
@@ -197,7 +208,8 @@ struct Chunk { long long r_lo, r_hi; cudaEvent_t ev; };
 // Copies the packed rows [0, nrows) from d_packed to h_packed in `nchunks` pieces on `st` (events recorded after each),
 // and expands every piece into H / P on `threads` host threads while the later pieces are still in flight.
 int copy_and_expand(const unsigned char* d_packed, unsigned char* h_packed, long long packed_pitch, long long nrows, long long cols,
-                    int32_t* H, int32_t* P, long long pitch, cudaStream_t st, int device, int threads, int nchunks)
+                    int32_t* H, int32_t* P, long long pitch, const int32_t* row_base, cudaStream_t st, int device, int threads,
+                    int nchunks)
 {
     if (threads <= 0) threads = swb_host_threads();
     nchunks = (int)std::max<long long>(1, std::min<long long>(nchunks, nrows));
@@ -224,7 +236,7 @@ int copy_and_expand(const unsigned char* d_packed, unsigned char* h_packed, long
                     if (cudaEventSynchronize(chunks[k].ev) != cudaSuccess) { failed.store(1); return; }
                     const long long rows = chunks[k].r_hi - chunks[k].r_lo;
                     expand_rows_range(h_packed, packed_pitch, chunks[k].r_lo + rows * t / threads,
-                                      chunks[k].r_lo + rows * (t + 1) / threads, cols, H, P, pitch, avx2);
+                                      chunks[k].r_lo + rows * (t + 1) / threads, cols, H, P, pitch, avx2, row_base);
                 }
             });
         for (auto& th : pool) th.join();
@@ -234,3 +246,57 @@ int copy_and_expand(const unsigned char* d_packed, unsigned char* h_packed, long
 }
 
 }  // namespace swb_packed
+
+// ---- whole delivery: rows [0, nrows) x columns [0, cols) of the device matrices into host int32 matrices
+extern "C" {
+
+size_t swb_d2h_packed_scratch_bytes(int64_t nrows, int64_t cols)
+{
+    if (nrows <= 0 || cols <= 0) return 0;
+    const size_t packed = (size_t)swb_packed_pitch(cols) * (size_t)nrows;
+    return packed + (((size_t)nrows * sizeof(int32_t) + 255) & ~(size_t)255) + 256;      // packed rows | row bases | flag
+}
+
+int swb_d2h_packed(const int32_t* dH, const int32_t* dP, int64_t pitch, int64_t nrows, int64_t cols,
+                   int32_t* H, int32_t* P, int64_t host_pitch, void* d_scratch, void* h_scratch, int threads, int device,
+                   void* stream)
+{
+    if (!dH || !dP || !d_scratch || !h_scratch || nrows <= 0 || cols <= 0 || pitch < cols || host_pitch < cols) return SWB_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_scratch) | reinterpret_cast<uintptr_t>(h_scratch)) & 15u) return SWB_ERR_ALIGN;
+    if (!H && !P) return SWB_OK;
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) return SWB_ERR_CUDA;
+    if (cur != device && cudaSetDevice(device) != cudaSuccess) return SWB_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long pp = swb_packed_pitch(cols);
+    const size_t packed_bytes = (size_t)pp * (size_t)nrows;
+    const size_t base_bytes = ((size_t)nrows * sizeof(int32_t) + 255) & ~(size_t)255;
+    unsigned char* d_packed = static_cast<unsigned char*>(d_scratch);
+    unsigned char* h_packed = static_cast<unsigned char*>(h_scratch);
+    int32_t* d_base = reinterpret_cast<int32_t*>(d_packed + packed_bytes);
+    int32_t* h_base = reinterpret_cast<int32_t*>(h_packed + packed_bytes);
+    int* d_flag = reinterpret_cast<int*>(d_packed + packed_bytes + base_bytes);
+    int* h_flag = reinterpret_cast<int*>(h_packed + packed_bytes + base_bytes);
+    int rc = SWB_OK;
+    auto fail = [&](int code) { if (cur != device) cudaSetDevice(cur); return code; };
+    if (cudaMemsetAsync(d_flag, 0, sizeof(int), st) != cudaSuccess) return fail(SWB_ERR_CUDA);
+    rc = swb_pack_rows_async(dH, dP, pitch, 0, nrows, cols, d_packed, pp, d_flag, d_base, device, st);
+    if (rc != SWB_OK) return fail(rc);
+    // the row bases and the flag sit behind the packed rows: one small copy, then the verdict
+    if (cudaMemcpyAsync(h_base, d_base, base_bytes + sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+        return fail(SWB_ERR_CUDA);
+    if (*h_flag == 0) {
+        rc = swb_packed::copy_and_expand(d_packed, h_packed, pp, nrows, cols, H, P, host_pitch, h_base, st, device, threads, 24);
+    } else {
+        // some row step of H or some P value does not fit the byte format (exotic scoring): plain copies
+        cudaError_t e = cudaSuccess;
+        if (H) e = cudaMemcpy2DAsync(H, (size_t)host_pitch * 4, dH, (size_t)pitch * 4, (size_t)cols * 4, (size_t)nrows, cudaMemcpyDeviceToHost, st);
+        if (P && e == cudaSuccess) e = cudaMemcpy2DAsync(P, (size_t)host_pitch * 4, dP, (size_t)pitch * 4, (size_t)cols * 4, (size_t)nrows, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = SWB_ERR_CUDA;
+    }
+    return fail(rc);
+}
+
+}  // extern "C"

@@ -25,15 +25,15 @@ def test_expand_rows_matches_the_format(swb, rows, cols, threads):
     packed = np_pack(H, P, ppitch)
     for pitch in (cols, cols + 5):
         H2 = np.full((rows, pitch), -777, np.int32); P2 = np.full((rows, pitch), -777, np.int32)
-        swb.expand_rows(packed, ppitch, rows, cols, H2, P2, pitch, threads)
+        swb.expand_rows(packed, ppitch, rows, cols, H2, P2, pitch, None, threads)
         assert (H2[:, :cols] == H).all() and (P2[:, :cols] == P).all()
         assert (H2[:, cols:] == -777).all() and (P2[:, cols:] == -777).all()      # the padding stays untouched
         # either output may be left out
         H3 = np.full((rows, pitch), -777, np.int32)
-        swb.expand_rows(packed, ppitch, rows, cols, H3, None, pitch, threads)
+        swb.expand_rows(packed, ppitch, rows, cols, H3, None, pitch, None, threads)
         assert (H3[:, :cols] == H).all()
         P3 = np.full((rows, pitch), -777, np.int32)
-        swb.expand_rows(packed, ppitch, rows, cols, None, P3, pitch, threads)
+        swb.expand_rows(packed, ppitch, rows, cols, None, P3, pitch, None, threads)
         assert (P3[:, :cols] == P).all()
 
 
@@ -49,7 +49,7 @@ def test_expand_rows_unaligned_outputs(swb):
         for off_p in (0, 3):
             bufH = np.full(rows * cols + 16, -1, np.int32); bufP = np.full(rows * cols + 16, -1, np.int32)
             H2 = bufH[off_h: off_h + rows * cols].reshape(rows, cols); P2 = bufP[off_p: off_p + rows * cols].reshape(rows, cols)
-            swb.expand_rows(packed, ppitch, rows, cols, H2, P2, cols, 1)
+            swb.expand_rows(packed, ppitch, rows, cols, H2, P2, cols, None, 1)
             assert (H2 == H).all() and (P2 == P).all()
             assert (bufH[:off_h] == -1).all() and (bufH[off_h + rows * cols:] == -1).all()
 
@@ -64,18 +64,34 @@ def test_oracle_matrices_fit_the_format(swb, oracle):
         assert d.min() >= -2 and d.max() <= 5 and P.min() >= -3 and P.max() <= 3
         ppitch = swb.packed_pitch(m + 1)
         H2 = np.empty_like(H); P2 = np.empty_like(P)
-        swb.expand_rows(np_pack(H, P, ppitch), ppitch, n + 1, m + 1, H2, P2, m + 1, 2)
+        swb.expand_rows(np_pack(H, P, ppitch), ppitch, n + 1, m + 1, H2, P2, m + 1, None, 2)
         assert (H2 == H).all() and (P2 == P).all()
+
+
+def test_expand_rows_with_row_base(swb):
+    # a sub-matrix whose first column is not 0 (a column strip): column 0's step is stored as 0, the base carries it
+    rng = np.random.default_rng(9)
+    rows, cols = 13, 301
+    base = rng.integers(0, 70000, rows).astype(np.int32)
+    steps = rng.integers(-2, 6, (rows, cols)); steps[:, 0] = 0
+    H = (base[:, None] + np.cumsum(steps, axis=1)).astype(np.int32)
+    P = rng.integers(-3, 4, (rows, cols)).astype(np.int32)
+    ppitch = swb.packed_pitch(cols)
+    packed = np.zeros((rows, ppitch), np.uint8)
+    packed[:, :cols] = ((steps + 16).astype(np.uint8) << 3) | (P + 3).astype(np.uint8)
+    H2 = np.empty_like(H); P2 = np.empty_like(P)
+    swb.expand_rows(packed, ppitch, rows, cols, H2, P2, cols, base, 3)
+    assert (H2 == H).all() and (P2 == P).all()
 
 
 def test_expand_rows_argument_errors(swb):
     buf = np.zeros(64, np.uint8); H = np.zeros(8, np.int32)
     with pytest.raises(swb.SwbError):
-        swb.expand_rows(buf, 4, 1, 8, H, None, 8, 1)       # packed pitch < cols
+        swb.expand_rows(buf, 4, 1, 8, H, None, 8, None, 1)       # packed pitch < cols
     with pytest.raises(swb.SwbError):
-        swb.expand_rows(buf, 64, 1, 8, H, None, 4, 1)      # pitch < cols
+        swb.expand_rows(buf, 64, 1, 8, H, None, 4, None, 1)      # pitch < cols
     with pytest.raises(swb.SwbError):
-        swb.expand_rows(None, 64, 1, 8, H, None, 8, 1)
+        swb.expand_rows(None, 64, 1, 8, H, None, 8, None, 1)
 
 
 @pytest.mark.gpu
@@ -102,8 +118,37 @@ def test_device_pack_round_trip(swb, oracle):
         packed = d_packed.cpu().numpy().reshape(n + 1, ppitch)
         assert (packed[:, :pitch] == np_pack(Ho, Po, ppitch)[:, :pitch]).all()
         H = np.empty((n + 1, pitch), np.int32); P = np.empty_like(H)
-        swb.expand_rows(packed, ppitch, n + 1, pitch, H, P, pitch, 3)
+        swb.expand_rows(packed, ppitch, n + 1, pitch, H, P, pitch, None, 3)
         assert (H == Ho).all() and (P == Po).all()
+
+
+@pytest.mark.gpu
+def test_d2h_packed_sub_matrix_with_row_base(swb, oracle):
+    # a block of columns of a real fill (what a column strip delivers): first column far from 0, own host pitch
+    torch = pytest.importorskip("torch")
+    m, n, c0, w = 2000, 900, 777, 1001
+    a, b = swb.generate(5, m, n)
+    Ho, Po, mpo = oracle.fill(np.frombuffer(a, np.uint8), np.frombuffer(b, np.uint8))
+    oracle.backtrack(Po, mpo)
+    pitch = m + 1
+    dH = torch.empty((n + 1) * pitch, dtype=torch.int32, device="cuda:0"); dP = torch.empty_like(dH)
+    assert swb.smithWaterman(a, b, m, n, dH, dP) == mpo
+    swb.backtrack(dP, pitch, mpo)
+    nbytes = swb.d2h_packed_scratch_bytes(n + 1, w)
+    d_scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda:0")
+    h_scratch = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    hp = w + 3
+    H = np.full((n + 1, hp), -7, np.int32); P = np.full((n + 1, hp), -7, np.int32)
+    swb.d2h_packed(dH[c0:], dP[c0:], pitch, n + 1, w, H, P, hp, d_scratch, h_scratch, threads=3,
+                   stream=torch.cuda.current_stream())
+    assert (H[:, :w] == Ho[:, c0:c0 + w]).all() and (P[:, :w] == Po[:, c0:c0 + w]).all()
+    assert (H[:, w:] == -7).all() and (P[:, w:] == -7).all()
+    # values that do not fit: the same call delivers through the plain copies
+    dH[5 * pitch + c0 + 10] += 1000
+    Ho2 = Ho.copy(); Ho2[5, c0 + 10] += 1000
+    swb.d2h_packed(dH[c0:], dP[c0:], pitch, n + 1, w, H, P, hp, d_scratch, h_scratch, stream=torch.cuda.current_stream())
+    assert (H[:, :w] == Ho2[:, c0:c0 + w]).all() and (P[:, :w] == Po[:, c0:c0 + w]).all()
+    assert (H[:, w:] == -7).all()
 
 
 @pytest.mark.gpu
