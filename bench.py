@@ -362,6 +362,31 @@ def secondary_single_gpu(swb, torch, dev, local, peak):
         del dH, dP
     # batch: 65536 x 256x256 in one launch (BASELINE configs[4]); sharded pair-wise when N > 1
     out["batch"] = batch_record(swb, torch, dev, local, peak, 0, 65536)
+    # several LARGE pairs through the variable-length batch entry point: single-pair kernel, two internal streams
+    try:
+        c = r = 45000; npairs = 4
+        a, b = swb.generate(SEED, c, r)
+        A = torch.frombuffer(bytearray(a * npairs), dtype=torch.uint8).to(dev); B = torch.frombuffer(bytearray(b * npairs), dtype=torch.uint8).to(dev)
+        size = ((c + 1) * (r + 1) + 3) // 4 * 4
+        dH = torch.empty(npairs * size, dtype=torch.int32, device=dev); dP = torch.empty_like(dH)
+        pos = torch.zeros(npairs, dtype=torch.int64, device=dev); sc = torch.zeros(npairs, dtype=torch.int32, device=dev)
+        offs = lambda step: [k * step for k in range(npairs)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for _ in range(4):
+            e0.record(stream)
+            swb.fill_pairs_async(A, offs(c), [c] * npairs, B, offs(r), [r] * npairs, offs(size), dH, dP, pos, sc, device=local, stream=stream)
+            e1.record(stream); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        out["large_pairs"] = {"workload": f"{npairs} pairs of {c}x{r} through swb_fill_pairs_async (full fill + maxPos per pair; consecutive "
+                                          "pairs overlap on two internal streams)",
+                              "ms_total": best, "ms_per_pair": best / npairs, "gcups": npairs * c * r / best / 1e6,
+                              "hbm_frac": 8.0 * npairs * (c + 1) * (r + 1) / best / 1e6 / peak,
+                              "maxPos": sorted(set(int(x) for x in pos.tolist()))}
+        del dH, dP
+    except Exception as e:
+        out["large_pairs"] = {"error": repr(e)[:200]}
     return out
 
 
@@ -441,15 +466,22 @@ def run_single(args, torch, swb, dev, local):
     pipelined = not args.no_pipeline
     total_ms = serial_total_ms
     fill_ms_serial = list(fill_ms)
+    nsets = 1
     if pipelined:
         try:
-            dH2 = torch.empty(cells_padded, dtype=torch.int32, device=dev)
-            dP2 = torch.empty(cells_padded, dtype=torch.int32, device=dev)
+            extra = [(torch.empty(cells_padded, dtype=torch.int32, device=dev), torch.empty(cells_padded, dtype=torch.int32, device=dev),
+                      torch.zeros(2, dtype=torch.int64, device=dev)) for _ in range(2)]
         except torch.cuda.OutOfMemoryError:
             pipelined = False
     if pipelined:
-        sets = [(dH, dP, d_scal), (dH2, dP2, torch.zeros(2, dtype=torch.int64, device=dev))]
-        s_fill = torch.cuda.Stream(device=dev)
+        # three H/P buffer sets, two fill streams: the fills of consecutive steps alternate between the streams, so the
+        # first strips of step k+1 run on the SMs that the ramp-down of step k's wavefront leaves idle (a single fill
+        # keeps the 296 strip slots 61 % busy: DESIGN.md section 4); the backtrack of step k runs on a third,
+        # high-priority stream.  Set k % 3 is reused by step k+3 after the backtrack of step k.
+        sets = [(dH, dP, d_scal)] + extra
+        nsets = len(sets)
+        s_fills = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        s_fill = s_fills[0]
         s_bt = torch.cuda.Stream(device=dev, priority=-1)
         ptimers = [swb.KernelTimer(local) for _ in range(args.steps)]
 
@@ -457,31 +489,38 @@ def run_single(args, torch, swb, dev, local):
             e_fill = [torch.cuda.Event() for _ in range(nsteps)]
             e_bt = [torch.cuda.Event() for _ in range(nsteps)]
             for k in range(nsteps):
-                H_, P_, sc_ = sets[k % 2]
-                if k >= 2:
-                    s_fill.wait_event(e_bt[k - 2])                 # this buffer set is free again
-                swb.fill_async(a_d, cols, b_d, rows, H_, P_, cols + 1, sc_[0:1], None, device=local, stream=s_fill,
+                H_, P_, sc_ = sets[k % nsets]
+                sf = s_fills[k % 2]
+                if k >= nsets:
+                    sf.wait_event(e_bt[k - nsets])                 # this buffer set is free again
+                swb.fill_async(a_d, cols, b_d, rows, H_, P_, cols + 1, sc_[0:1], None, device=local, stream=sf,
                                warps_per_band=args.wpc, timer=ptimers[k] if use_timers else None)
-                e_fill[k].record(s_fill)
+                e_fill[k].record(sf)
                 s_bt.wait_event(e_fill[k])
                 swb.backtrack_async(P_, cols + 1, d_maxPos=sc_[0:1], d_pathLen=sc_[1:2], device=local, stream=s_bt)
                 e_bt[k].record(s_bt)
-            for k in range(max(0, nsteps - 2), nsteps):
+            for k in range(max(0, nsteps - nsets), nsteps):        # join: the region ends when the last backtracks have
                 s_fill.wait_event(e_bt[k])
 
-        run_pipeline(max(args.warmup, 2), False)
+        run_pipeline(max(args.warmup, 3), False)
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         p0.record(s_fill)
+        s_fills[1].wait_event(p0)
         run_pipeline(args.steps, True)
         p1.record(s_fill)
         barrier()
         total_ms = p0.elapsed_time(p1)
         fill_ms = [t.elapsed_ms() for t in ptimers]
-        for (_, _, sc_) in sets[:min(2, args.steps)]:
+        for (_, _, sc_) in sets[:min(nsets, args.steps)]:
             assert (int(sc_[0]), int(sc_[1])) == (maxPos, plen), "pipelined steps disagree with the serial ones"
-        del dH2, dP2, sets
+        # the last results of the overlapped region against the oracle's digests (every set that was written)
+        if g is not None:
+            for (H_, P_, _) in sets[1:min(nsets, args.steps)]:
+                c2, b2 = check_digests(g, H_.view(rows + 1, cols + 1), P_.view(rows + 1, cols + 1).abs(), 0, cols)
+                parity["digests_checked"] += c2; parity["digest_mismatches"] += b2
+        del extra, sets
     # clocks: sampled over a separate, long enough run of the fill (the timed regions above last tens of milliseconds)
     sampler = ClockSampler(local)
     sampler.start()
@@ -512,7 +551,11 @@ def run_single(args, torch, swb, dev, local):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_source, "kernel": "swb_tall::fill_kernel<64,true,true> (96-row strips, half skew, score look-up)",
                 "kernel_ms_avg": fill_avg, "kernel_ms_min": min(fill_ms_serial), "kernel_ms_avg_in_pipelined_region": statistics.mean(fill_ms),
-                "timed_in": "the K one-at-a-time timed steps (`serial`), CUDA events around the launch on its stream",
+                "timed_in": "the K one-at-a-time timed steps (`serial`), CUDA events around the launch on its stream: ONE launch alone on the GPU",
+                "sustained": ({"achieved": 8 * cells_padded / (ms_per_step * 1e-3) / 1e9, "frac": 8 * cells_padded / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "what": "algorithmic bytes of the K launches / the timed region of the K overlapped steps (everything else in a "
+                                       "step included): two launches are in flight at a time, each launch takes longer than ms_per_step "
+                                       "(kernel_ms_avg_in_pipelined_region) while the GPU retires one every ms_per_step"} if pipelined else None),
                 "algorithmic_bytes_per_launch": 8 * cells_padded,
                 "peak_source": peak_src, "fill_gcups": cols * rows / (fill_avg * 1e-3) / 1e9}
 
@@ -587,9 +630,11 @@ def run_single(args, torch, swb, dev, local):
                        "seed": SEED, "scoring": [3, -3, -2], "pairs": 1,
                        "l2": "each step writes 16.2 GB of H+P (>> 126 MB L2); no flush needed",
                        "parallelism": "1 GPU",
-                       "pipeline": ("two H/P buffer sets: the backtrack of step k (one SM, high-priority stream) "
-                                    "overlaps the fill of step k+1; every step does all of its work inside the timed "
-                                    "region" if pipelined else "none: fill, maxPos, backtrack back to back")},
+                       "pipeline": ("three H/P buffer sets, two fill streams + one backtrack stream: consecutive steps overlap -- "
+                                    "the first strips of step k+1 run on the SMs the ramp-down of step k's wavefront leaves "
+                                    "idle, the backtrack of step k (one SM) runs beside them; every step does all of its work "
+                                    "inside the timed region, which ends when the last backtrack has finished; `serial` is "
+                                    "one step at a time" if pipelined else "none: fill, maxPos, backtrack back to back")},
             "serial": {"ms_per_step": serial_total_ms / args.steps,
                        "value": cols * rows / (serial_total_ms / args.steps * 1e-3) / 1e9,
                        "what": "the same K steps one at a time on one stream (latency of a step)"},

@@ -189,8 +189,11 @@ int swb_fill_batch_async(const char* a, int64_t m, const char* b, int64_t n, int
  * a / b (host or device concatenations), m / n = its lengths, hp_off = int32 offset of its matrices in dH / dP (a
  * multiple of 4; the matrices have the single-pair layout with pitch m[k]+1).  Runs of consecutive pairs with the
  * same shape, packed sequences and a uniform matrix stride go out as ONE batched launch (the 65536 x 256x256
- * configuration is a single run); other pairs get a launch each.  d_maxPos / d_maxScore: DEVICE arrays of npairs
- * entries (maxPos relative to the pair's own matrix) or NULL. */
+ * configuration is a single run); other pairs get a launch each.  LARGE pairs (n >= 14208 rows and m >= 4096: one
+ * pair alone covers half of the GPU's strip slots) always run one by one on the single-pair kernel, alternating
+ * between two internal streams that fork from and join into `stream`: the wavefront of pair k+1 starts on the SMs
+ * the ramp-down of pair k leaves idle (45000 x 45000: 4.60 -> 3.66 ms per pair).  The call stays asynchronous.
+ * d_maxPos / d_maxScore: DEVICE arrays of npairs entries (maxPos relative to the pair's own matrix) or NULL. */
 int swb_fill_pairs_async(const char* a, const int64_t* a_off, const int64_t* m,
                          const char* b, const int64_t* b_off, const int64_t* n,
                          const int64_t* hp_off, int64_t npairs, const swb_scoring* scoring,

@@ -127,6 +127,23 @@ struct StripLink {                         // column-strip mode (nullptr members
 
 }  // namespace
 
+// Two library-owned streams per device for swb_fill_pairs_async (created on first use, kept for the life of the
+// process like the workspace pool).  Streams created and destroyed inside a call did not run concurrently with each
+// other (two 45000 x 45000 pairs: 11.3 ms against 7.8 ms on long-lived streams).
+static bool side_streams(int device, cudaStream_t out[2])
+{
+    static std::mutex mu;
+    static cudaStream_t table[64][2] = {};
+    if (device < 0 || device >= 64) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int q = 0; q < 2; ++q)
+        if (!table[device][q] && cudaStreamCreateWithFlags(&table[device][q], cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError(); table[device][q] = nullptr; return false;
+        }
+    out[0] = table[device][0]; out[1] = table[device][1];
+    return true;
+}
+
 // The fill's host side, once per kernel geometry (see swb_fill_impl.inc)
 namespace swb {
 #include "swb_fill_impl.inc"
@@ -266,23 +283,63 @@ int swb_fill_pairs_async(const char* a, const int64_t* a_off, const int64_t* m,
                          int32_t* dH, int32_t* dP, int64_t* d_maxPos, int32_t* d_maxScore, int device, void* stream)
 {
     if (!a || !a_off || !m || !b || !b_off || !n || !hp_off || npairs <= 0 || !dH || !dP) return SWB_ERR_ARG;
-    int64_t k = 0;
-    while (k < npairs) {
-        // the longest run of equally shaped pairs with packed sequences and a uniform matrix stride
+    // Large pairs (one pair alone covers at least half of the GPU's 296 strip slots) run one by one on the single-pair
+    // geometry, alternating between two internal streams: the first strips of pair k+1 take the SMs that the ramp-down
+    // of pair k's wavefront leaves idle (measured, 45000 x 45000: 4.60 -> 3.66 ms per pair = 68 % of the HBM peak
+    // sustained).  The internal streams fork from and join into the caller's stream, so the call stays asynchronous.
+    auto large = [&](int64_t i) { return n[i] >= 148 * 96 && m[i] >= 4096; };
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    int64_t nlarge = 0;
+    for (int64_t i = 0; i < npairs; ++i) nlarge += large(i) ? 1 : 0;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        for (int q = 0; q < 2; ++q) if (join[q]) cudaEventDestroy(join[q]);
+        if (fork) cudaEventDestroy(fork);
+    };
+    if (nlarge >= 2 && side_streams(device, side)) {
+        cudaError_t e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        for (int q = 0; q < 2 && e == cudaSuccess; ++q) e = cudaEventCreateWithFlags(&join[q], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(fork, user);
+        for (int q = 0; q < 2 && e == cudaSuccess; ++q) e = cudaStreamWaitEvent(side[q], fork, 0);
+        if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "swb_fill_pairs_async streams", __LINE__); }
+    } else {
+        side[0] = side[1] = nullptr;
+    }
+    int rc = SWB_OK;
+    int64_t k = 0, large_seen = 0;
+    while (k < npairs && rc == SWB_OK) {
+        if (hp_off[k] & 3) { rc = SWB_ERR_ALIGN; break; }
+        if (large(k)) {
+            cudaStream_t st = side[0] ? side[large_seen++ & 1] : user;
+            rc = fill_impl(a + a_off[k], m[k], b + b_off[k], n[k], 1, scoring, dH + hp_off[k], dP + hp_off[k], m[k] + 1, 0,
+                           d_maxPos ? d_maxPos + k : nullptr, d_maxScore ? d_maxScore + k : nullptr, device, st, nullptr, true);
+            ++k;
+            continue;
+        }
+        // the longest run of equally shaped (small) pairs with packed sequences and a uniform matrix stride: one launch
         int64_t run = 1, stride = 0;
         if (k + 1 < npairs) stride = hp_off[k + 1] - hp_off[k];
-        while (k + run < npairs && m[k + run] == m[k] && n[k + run] == n[k] &&
+        while (k + run < npairs && !large(k + run) && m[k + run] == m[k] && n[k + run] == n[k] &&
                a_off[k + run] - a_off[k + run - 1] == m[k] && b_off[k + run] - b_off[k + run - 1] == n[k] &&
                hp_off[k + run] - hp_off[k + run - 1] == stride && stride >= (n[k] + 1) * (m[k] + 1))
             ++run;
-        if (hp_off[k] & 3) return SWB_ERR_ALIGN;
-        const int rc = fill_impl(a + a_off[k], m[k], b + b_off[k], n[k], run, scoring, dH + hp_off[k], dP + hp_off[k],
-                                 m[k] + 1, run > 1 ? stride : 0, d_maxPos ? d_maxPos + k : nullptr,
-                                 d_maxScore ? d_maxScore + k : nullptr, device, stream, nullptr, true);
-        if (rc != SWB_OK) return rc;
+        rc = fill_impl(a + a_off[k], m[k], b + b_off[k], n[k], run, scoring, dH + hp_off[k], dP + hp_off[k],
+                       m[k] + 1, run > 1 ? stride : 0, d_maxPos ? d_maxPos + k : nullptr,
+                       d_maxScore ? d_maxScore + k : nullptr, device, user, nullptr, true);
         k += run;
     }
-    return SWB_OK;
+    if (side[0]) {
+        // join (also after an error: whatever was enqueued on the side streams must not outlive the call's ordering)
+        for (int q = 0; q < 2; ++q)
+            if (cudaEventRecord(join[q], side[q]) != cudaSuccess || cudaStreamWaitEvent(user, join[q], 0) != cudaSuccess) {
+                if (rc == SWB_OK) rc = cuda_fail(cudaGetLastError(), "swb_fill_pairs_async join", __LINE__);
+            }
+    }
+    cleanup();
+    return rc;
 }
 
 int swb_shard_pairs(int64_t npairs, int nshards, int shard, int64_t* first, int64_t* count)

@@ -998,7 +998,10 @@ __device__ __forceinline__ void writer_strip(const FillParams& p, const long lon
     const int cl  = rho / kR;
     const long long row = r0 + rho;
     const bool myrow = lane < kWRows && row <= p.n;
-    const int ph = (int)((row * p.pitch) & 31);
+    // (the phase of the row's first element within its 128-byte line counts the base address too: pair k of a batch
+    //  starts pair_stride ints after pair 0, a 16-byte aligned but in general not a 128-byte aligned address -- with the
+    //  phase taken from row * pitch alone every "line" store of such a pair straddled two lines)
+    const int ph = (int)((((unsigned long long)p.H >> 2) + (unsigned long long)(row * p.pitch)) & 31);
     const int d  = (kSkewCols * cl + 31 - ph) >> 5;               // (lane cl has finished column 32r + 31 - kSkewCols*cl by the end of group r)
     const int E  = 32 * d + ph;
     const long long G0 = row * p.pitch - E;                      // multiple of 32

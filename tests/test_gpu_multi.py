@@ -85,6 +85,52 @@ def test_variable_length_pairs(swb, oracle):
             assert int(d_pos[k]) == mpo and int(d_sc[k]) == (Ho.reshape(-1)[mpo] if mpo else 0)
 
 
+def test_large_pairs_overlap_on_two_streams(swb, oracle):
+    # pairs with n >= 14208 and m >= 4096 leave the batched launch: single-pair kernel, two internal streams that
+    # fork from / join into the caller's stream.  Mixed with small pairs; results against the oracle (maxPos, score,
+    # digests of H and P per pair) and against a plain single fill of the same pair.
+    from oracle.digest import digest_np, digest_torch
+    dev = torch.device("cuda:0")
+    shapes = [(4100, 14300), (300, 200), (4096, 14208), (300, 200), (5000, 15000)]
+    seqs = [make_pair(40 + k, m, n) for k, (m, n) in enumerate(shapes)]
+    A = b"".join(s[0] for s in seqs); B = b"".join(s[1] for s in seqs)
+    a_off = np.cumsum([0] + [s[0] for s in shapes[:-1]]).tolist(); b_off = np.cumsum([0] + [s[1] for s in shapes[:-1]]).tolist()
+    sizes = [((m + 1) * (n + 1) + 3) // 4 * 4 for (m, n) in shapes]
+    hp_off = np.cumsum([0] + sizes[:-1]).tolist()
+    dH = torch.full((sum(sizes),), -9, dtype=torch.int32, device=dev); dP = torch.full_like(dH, -9)
+    d_pos = torch.zeros(len(shapes), dtype=torch.int64, device=dev); d_sc = torch.zeros(len(shapes), dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    for rnd in range(2):
+        swb.fill_pairs_async(A, a_off, [x[0] for x in shapes], B, b_off, [x[1] for x in shapes], hp_off, dH, dP, d_pos, d_sc, stream=s)
+        # work enqueued on the caller's stream AFTER the call must see the results (the side streams have joined)
+        with torch.cuda.stream(s):
+            pos = d_pos.clone(); last = [dH[hp_off[k] + (x[0] + 1) * (x[1] + 1) - 1].clone() for k, x in enumerate(shapes)]
+        s.synchronize()
+        for k, (m, n) in enumerate(shapes):
+            a, b = seqs[k]
+            if rnd == 0:
+                mso, mpo = oracle.score_only(a, b)
+                assert int(pos[k]) == mpo and int(d_sc[k]) == mso, k
+            mpo = int(pos[k])
+            assert int(last[k]) != -9, k                          # the last cell of the pair was written before the join
+            Hk = dH[hp_off[k]:hp_off[k] + (m + 1) * (n + 1)].view(n + 1, m + 1); Pk = dP[hp_off[k]:hp_off[k] + (m + 1) * (n + 1)].view(n + 1, m + 1)
+            H1 = torch.empty((n + 1) * (m + 1), dtype=torch.int32, device=dev); P1 = torch.empty_like(H1)
+            assert swb.fill(a, m, b, n, H1, P1) == mpo
+            assert bool((Hk.reshape(-1) == H1).all()) and bool((Pk.reshape(-1) == P1).all()), k
+            if rnd == 1:
+                continue
+            if n < 1000:
+                Ho, Po, _ = oracle.fill(a, b)
+                assert (Hk.cpu().numpy() == Ho).all() and (Pk.cpu().numpy() == Po).all()
+            else:
+                for i0, i1, Hb, Pb in oracle.fill_blocks(a, b, 4096):
+                    if i0 is None:
+                        break
+                    assert digest_torch(Hk[i0:i1], i0, 0) == digest_np(Hb, i0, 0), (k, i0)
+                    assert digest_torch(Pk[i0:i1], i0, 0) == digest_np(Pb, i0, 0), (k, i0)
+        dH.fill_(-9); dP.fill_(-9)
+
+
 def cli(args, env_extra=None):
     env = dict(os.environ); env.update(env_extra or {})
     p = subprocess.run([str(ROOT / "smith-waterman_b200" / "swb")] + args, capture_output=True, text=True, env=env, timeout=300)
