@@ -21,7 +21,7 @@ value  = cols*rows / max-over-ranks(step time) / 1e9 with the sequences already 
          timed steps run as a pipeline over two H/P buffer sets: the backtrack of step k (a serial
          pointer chase that occupies one SM) overlaps the fill of step k+1 on a second stream; nothing
          is skipped.  `serial` repeats the measurement one step at a time (the latency of a step).
-         At N>1 the same pipeline runs over two sets of strip buffers per GPU;
+         At N>1 the same pipeline runs over three sets of strip buffers per GPU;
 e2e    = the same metric through the host-buffer C-ABI call (swb_ctx_align): H2D of a and
          b, fill, backtrack and the delivery of int32 H and P (16.2 GB) into the caller's pinned host
          buffers inside the timed region.  The library moves one byte per cell over PCIe (row step of
@@ -75,6 +75,7 @@ def parse_args():
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (batch, score-only, skewed, replicas)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: consecutive fills on ONE stream (no overlap of steps k and k+1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="report the one-pair-at-a-time figure as `value`")
     ap.add_argument("--wpc", type=int, default=0, help="warps per band override (0 = library default)")
@@ -716,21 +717,28 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
     # backtrack hops of step k run on a second stream while the fill kernels of step k+1 are already running; every step
     # still does all of its work and the timed region ends when the last backtrack has finished.
     pipelined = not args.no_pipeline
-    pipe2 = None
+    extra_pipes = []
     if pipelined:
         try:
-            pipe2 = strips.StripPipeline(a, b, local)
-        except Exception:                                   # not enough device memory for a second buffer set
+            extra_pipes = [strips.StripPipeline(a, b, local), strips.StripPipeline(a, b, local)]
+        except Exception:                                   # not enough device memory for three buffer sets
             pipelined = False
     ok_t = torch.tensor([1 if pipelined else 0], dtype=torch.int64, device=dev)
     dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
     pipelined = bool(ok_t.item())
+    overlap_fills = pipelined and not args.no_overlap
     if pipelined:
-        pipes = [pipe, pipe2]
-        s_fill = torch.cuda.Stream(device=dev)
+        # three sets of strip buffers, two fill streams (as at N = 1): the fills of steps k and k+1 overlap on every GPU --
+        # a GPU whose strip of step k is done starts its strip of step k+1 while the GPUs to its right still work on
+        # step k (in column-strip mode every GPU idles for the hops before and after its own strip) -- and the maxPos
+        # all-gather + backtrack hops of step k-1 run on a third stream beside them.
+        pipes = [pipe] + extra_pipes
+        s_fills = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if overlap_fills else [torch.cuda.Stream(device=dev)] * 2
+        s_fill = s_fills[0]
         s_bt = torch.cuda.Stream(device=dev, priority=-1)
         ptimers = [swb.KernelTimer(local) for _ in range(args.steps)]
         presult = {}
+        lag = 2 if overlap_fills else 1                      # fills enqueued ahead of the step being finished
 
         def finish(pp, ev):
             with torch.cuda.stream(s_bt):
@@ -742,17 +750,20 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
         def run_pipeline(nsteps, use_timers):
             evs = [torch.cuda.Event() for _ in range(nsteps)]
             for k in range(nsteps):
-                pipes[k % 2].fill_async(stream=s_fill, timer=ptimers[k] if use_timers else None)
-                evs[k].record(s_fill)
-                if k >= 1:
-                    finish(pipes[(k - 1) % 2], evs[k - 1])
-            finish(pipes[(nsteps - 1) % 2], evs[nsteps - 1])
+                # (set k % 3 was last used by step k-3, whose maxPos gather and backtrack finished in iteration k-1)
+                pipes[k % 3].fill_async(stream=s_fills[k % 2], timer=ptimers[k] if use_timers else None)
+                evs[k].record(s_fills[k % 2])
+                if k >= lag:
+                    finish(pipes[(k - lag) % 3], evs[k - lag])
+            for k in range(max(0, nsteps - lag), nsteps):
+                finish(pipes[k % 3], evs[k])
 
-        run_pipeline(max(args.warmup, 2), False)
+        run_pipeline(max(args.warmup, 3), False)
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         p0.record(s_fill)
+        s_fills[1].wait_event(p0)
         run_pipeline(args.steps, True)
         p1.record(s_bt)
         barrier()
@@ -761,7 +772,9 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
         assert (presult["maxPos"], presult["path_len"]) == (maxPos, plen), "pipelined steps disagree with the serial ones"
         # leave `pipe` holding the result of a complete step (fill + backtrack) for the parity checks below
         step()
-        pipe2.close(); pipe2 = None
+        for pp in extra_pipes:
+            pp.close()
+        extra_pipes = []
         torch.cuda.empty_cache()
 
     # the path digest is checked after the last timed backtrack: gather the negated cells of every strip
@@ -961,8 +974,13 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
                                           "st.relaxed.sys over NVLink inside the fill kernel, per-32-row release flags; NCCL carries only the "
                                           "maxPos all-gather (3 int64 per rank) and one 3-word broadcast per backtrack hop",
                            "timing": "CUDA events on each rank's streams around the K steps, max over ranks; barrier + synchronize on both sides",
-                           "pipeline": ("two sets of strip buffers per GPU: the maxPos all-gather and the backtrack hops of step k run beside "
-                                        "the fill kernels of step k+1; every step does all of its work inside the timed region"
+                           "pipeline": (("three sets of strip buffers per GPU, two fill streams: the fills of steps k and k+1 overlap (a GPU "
+                                         "that has finished its strip of step k starts its strip of step k+1 while the GPUs to its right still "
+                                         "work on step k), the maxPos all-gather and the backtrack hops of step k-1 run beside them; "
+                                         if overlap_fills else
+                                         "three sets of strip buffers per GPU: the maxPos all-gather and the backtrack hops of step k run beside "
+                                         "the fill kernels of step k+1; ") +
+                                        "every step does all of its work inside the timed region, which ends when the last backtrack has finished"
                                         if pipelined else "none: fill, maxPos, backtrack back to back")},
                 "serial": {"ms_per_step": float(tmax[5].item()) / args.steps,
                            "value": cols * rows / (float(tmax[5].item()) / args.steps * 1e-3) / 1e9,
