@@ -1310,9 +1310,10 @@ fill_kernel(const FillParams p_in)
     // b of a pair is scheduled, its band b-1 finished a whole wave of CTAs earlier and its boundary row is complete, so
     // no CTA of a batch ever occupies an SM while it waits for the strip above (pair-major order: 4 chained CTAs per
     // 256-row pair, each idling ~40 steps + an L2 round trip behind the previous one).
-    // (Score-only batches: 7.40 -> 5.21 ms for 65536 x 256x256.  Batches WITH H/P stores keep the pair-major order: 11.8 ms
-    // against 12.4 band-major -- their boundary rows would spill from L2 to HBM and the writers bound them anyway.)
-    const bool band_major = !STORE && p_in.npairs > 1;
+    // (65536 x 256x256: score only 7.40 -> 5.21 ms, full fill 11.36 -> 9.07 ms.  An earlier measurement had the full fill
+    //  slower band-major (12.4 against 11.8 ms); it was taken while the writers' line phase ignored the base address of a
+    //  pair, see writer_strip.)
+    const bool band_major = p_in.npairs > 1;
     const long long pair = band_major ? (long long)(s_band % p_in.npairs) : (long long)(s_band / p_in.nbands);
     const int band = band_major ? (int)(s_band / p_in.npairs) : (s_band % p_in.nbands);
     FillParams p = p_in;
