@@ -13,8 +13,10 @@
  * them return 0 on success and a negative swb_status otherwise (the reference
  * prints and exit(0)s on CUDA errors, simple-cuda/sw-default-discrete.cu:101-108;
  * we never exit).  Calls on different streams/devices are independent; the only
- * process-wide state is one private CUDA memory pool per device for the per-call
- * workspace (it keeps at most 2 GB of freed blocks; the default pool is not touched).  There is NO CPU fallback: without a CUDA device every compute
+ * process-wide state is, per device, one private CUDA memory pool for the per-call
+ * workspace (it keeps at most 2 GB of freed blocks; the default pool is not touched)
+ * and two streams that swb_fill_pairs_async forks large pairs onto (created on
+ * first use).  There is NO CPU fallback: without a CUDA device every compute
  * entry point returns SWB_ERR_CUDA.
  *
  * Data contract (identical to the reference, omp_smithW.c:109-118,336):

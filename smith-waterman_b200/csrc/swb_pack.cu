@@ -192,8 +192,14 @@ int swb_expand_rows(const unsigned char* packed, int64_t packed_pitch, int64_t n
     if (threads == 1) { expand_rows_range(packed, packed_pitch, 0, nrows, cols, H, P, pitch, avx2, row_base); return SWB_OK; }
     std::vector<std::thread> pool;
     pool.reserve(threads);
-    for (int t = 0; t < threads; ++t)
-        pool.emplace_back([=] { expand_rows_range(packed, packed_pitch, nrows * t / threads, nrows * (t + 1) / threads, cols, H, P, pitch, avx2, row_base); });
+    int started = 0;
+    try {
+        for (int t = 0; t < threads; ++t, ++started)
+            pool.emplace_back([=] { expand_rows_range(packed, packed_pitch, nrows * t / threads, nrows * (t + 1) / threads, cols, H, P, pitch, avx2, row_base); });
+    } catch (...) {
+        // the host refused another thread: this thread does the slices that have no worker
+        expand_rows_range(packed, packed_pitch, nrows * started / threads, nrows, cols, H, P, pitch, avx2, row_base);
+    }
     for (auto& th : pool) th.join();
     return SWB_OK;
 }
@@ -227,18 +233,23 @@ int copy_and_expand(const unsigned char* d_packed, unsigned char* h_packed, long
     std::atomic<int> failed{err == cudaSuccess ? 0 : 1};
     if (!failed.load()) {
         const bool avx2 = have_avx2();
+        // worker t of `workers` expands slice t of every chunk as soon as the chunk has landed
+        auto work = [&](int t_lo, int t_hi) {
+            cudaSetDevice(device);
+            for (int k = 0; k < nchunks; ++k) {
+                if (cudaEventSynchronize(chunks[k].ev) != cudaSuccess) { failed.store(1); return; }
+                const long long rows = chunks[k].r_hi - chunks[k].r_lo;
+                expand_rows_range(h_packed, packed_pitch, chunks[k].r_lo + rows * t_lo / threads,
+                                  chunks[k].r_lo + rows * t_hi / threads, cols, H, P, pitch, avx2, row_base);
+            }
+        };
         std::vector<std::thread> pool;
         pool.reserve(threads);
-        for (int t = 0; t < threads; ++t)
-            pool.emplace_back([&, t] {
-                cudaSetDevice(device);
-                for (int k = 0; k < nchunks; ++k) {
-                    if (cudaEventSynchronize(chunks[k].ev) != cudaSuccess) { failed.store(1); return; }
-                    const long long rows = chunks[k].r_hi - chunks[k].r_lo;
-                    expand_rows_range(h_packed, packed_pitch, chunks[k].r_lo + rows * t / threads,
-                                      chunks[k].r_lo + rows * (t + 1) / threads, cols, H, P, pitch, avx2, row_base);
-                }
-            });
+        int started = 0;
+        try {
+            for (int t = 0; t + 1 < threads; ++t, ++started) pool.emplace_back(work, t, t + 1);
+        } catch (...) { }                                   // the host refused another thread: this one takes the rest
+        work(started, threads);
         for (auto& th : pool) th.join();
     }
     for (auto& c : chunks) if (c.ev) cudaEventDestroy(c.ev);
