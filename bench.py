@@ -774,7 +774,10 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
         step()
         for pp in extra_pipes:
             pp.close()
-        extra_pipes = []
+        # (drop every reference to the extra buffer sets -- 40 GB each at N = 2 -- before the legs below allocate theirs)
+        extra_pipes = []; pipes = None; pp = None
+        import gc
+        gc.collect()
         torch.cuda.empty_cache()
 
     # the path digest is checked after the last timed backtrack: gather the negated cells of every strip

@@ -200,6 +200,8 @@ class ColumnStrip:
                 if self.left_flags[k]:
                     lib.swb_ipc_free(self.left_flags[k], self.device)
             self.left_in, self.left_flags = [0, 0], [0, 0]
+        # the matrices go back to the allocator with the strip (tens of GB at the full-size configurations)
+        self.dH = self.dP = self.a_d = self.b_d = None
 
 
 # ----------------------------------------------------------------------------------------------
