@@ -271,7 +271,7 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------- helpers of our arm
-KERNELS_PER_FILL = ["prep_kernel", "selector_kernel", "fill_kernel<look-up>", "fill_kernel<compare> (returns at once)",
+KERNELS_PER_FILL = ["prep_kernel", "selector_kernel", "fill_kernel_form<look-up>", "fill_kernel_form<compare> (returns at once)",
                     "argmax_kernel", "finalize_kernel"]
 
 
@@ -550,7 +550,7 @@ def run_single(args, torch, swb, dev, local):
         except (ValueError, OSError):
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_source, "kernel": "swb_tall::fill_kernel<64,true,true> (96-row strips, half skew, score look-up)",
+                "traffic": traffic, "traffic_source": traffic_source, "kernel": "swb_tall::fill_kernel_form<64,true,true> (96-row strips, half skew, score look-up)",
                 "kernel_ms_avg": fill_avg, "kernel_ms_min": min(fill_ms_serial), "kernel_ms_avg_in_pipelined_region": statistics.mean(fill_ms),
                 "timed_in": "the K one-at-a-time timed steps (`serial`), CUDA events around the launch on its stream: ONE launch alone on the GPU",
                 "sustained": ({"achieved": 8 * cells_padded / (ms_per_step * 1e-3) / 1e9, "frac": 8 * cells_padded / (ms_per_step * 1e-3) / 1e9 / peak,
@@ -995,7 +995,7 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": nk * args.steps * world,
                 "kernels_per_step": KERNELS_PER_FILL + ["backtrack_kernel (on the ranks the path crosses)"],
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
-                             "traffic": None, "traffic_source": None, "kernel": "swb_tall::fill_kernel<64,true,true> (column-strip mode), all ranks",
+                             "traffic": None, "traffic_source": None, "kernel": "swb_tall::fill_kernel_form<64,true,true> (column-strip mode), all ranks",
                              "kernel_ms_avg": max(kernel_ms), "algorithmic_bytes_per_launch": 8 * cells_padded,
                              "peak_source": peak_src + f" x {world} GPUs",
                              "what": "bytes of all strips / slowest rank's fill kernel time / (N x measured HBM peak)"},

@@ -1,7 +1,10 @@
 // swb_api.cu -- thin C ABI over the sm_100a kernels (include/swb200.h).
 // Host code is plain C++/CUDA runtime; no torch types, no CPU fallback.
 #include "../../include/swb200.h"
+#define SWB_MERGED_FORMS 1              // (the batch geometry launches ONE fill kernel that holds both forms of the cell arithmetic)
 #include "swb_kernels.cuh"              // namespace swb: two rows per lane (batches, score-only) + backtrack, argmax ...
+#undef SWB_MERGED_FORMS
+#define SWB_MERGED_FORMS 0
 #include "swb_backtrack.cuh"
 #undef SWB_NS
 #undef SWB_ROWS_PER_LANE

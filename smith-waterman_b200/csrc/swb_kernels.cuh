@@ -1258,16 +1258,8 @@ __host__ __device__ constexpr size_t fill_smem_bytes(int wpc, int KT, bool store
 // STORE = false is the score-only variant: no staging, no writers, per-row best cells instead.
 // ---------------------------------------------------------------------------------
 template <int KT, bool STORE, bool PROF>
-__global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true), ((KT == 64 && STORE) || kR > 2) ? 1 : 2)
-fill_kernel(const FillParams p_in)
+__device__ __forceinline__ void fill_body(const FillParams& p_in)
 {
-    // Both instantiations are launched; the alphabet of b (counted on the device by selector_kernel, so that the call
-    // stays asynchronous for device-resident sequences) decides which one runs.
-#ifdef SWB_X_FORCE_COMPARE                                     // developer build: always the character-compare instantiation
-    if (PROF) return;
-#else
-    if ((p_in.prof_ok != 0 && *p_in.nletters <= kMaxLetters) != PROF) return;
-#endif
     extern __shared__ __align__(1024) int4 smem4[];
     __shared__ int s_band;
     __shared__ int s_staged[kMaxWpc], s_drained[kMaxWpc * kWriters], s_consumed[kMaxWpc + 1];
@@ -1450,6 +1442,44 @@ fill_kernel(const FillParams p_in)
         if (band == 0 || band_r0 > p.n) return;
         loader_band(p.boundary + (size_t)(band - 1) * p.bstride + kBoundaryPad, p.in_last, rings, lane, s_consumed);
     }
+}
+
+// The kernels.  The alphabet of b (counted on the device by selector_kernel, so that the call stays asynchronous for
+// device-resident sequences) decides which form of the cell arithmetic runs, the same in every thread of the grid.
+//  * fill_kernel<KT, STORE>: ONE launch holds both forms and branches (SWB_MERGED_FORMS, the batch geometry: two
+//    launches, one of which returns at once, cost the 65536-pair batch 0.14 ms of 9.07 -- 262 144 empty CTAs -- and the
+//    score-only batch 0.16 of 4.92 ms).
+//  * fill_kernel_form<KT, STORE, PROF>: one kernel per form, both launched, the one that does not apply returns at
+//    once (the single-pair geometries: there the merged kernel measured 1-4 % SLOWER on the chain-bound configurations
+//    -- score-only 45000 x 45000 3.64 -> 3.72 ms, 2 000 000 x 1000 51.8 -> 53.8 ms -- and an empty launch of 235 CTAs
+//    costs 3 us).
+#ifndef SWB_MERGED_FORMS
+#define SWB_MERGED_FORMS 0
+#endif
+constexpr bool kMergedForms = SWB_MERGED_FORMS != 0;
+
+template <int KT, bool STORE>
+__global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true), ((KT == 64 && STORE) || kR > 2) ? 1 : 2)
+fill_kernel(const FillParams p_in)
+{
+#ifdef SWB_X_FORCE_COMPARE                                     // developer build: always the character-compare form
+    fill_body<KT, STORE, false>(p_in);
+#else
+    if (p_in.prof_ok != 0 && *p_in.nletters <= kMaxLetters) fill_body<KT, STORE, true>(p_in);
+    else                                                    fill_body<KT, STORE, false>(p_in);
+#endif
+}
+
+template <int KT, bool STORE, bool PROF>
+__global__ void __launch_bounds__(fill_block_threads(kMaxWpc, true), ((KT == 64 && STORE) || kR > 2) ? 1 : 2)
+fill_kernel_form(const FillParams p_in)
+{
+#ifdef SWB_X_FORCE_COMPARE
+    if (PROF) return;
+#else
+    if ((p_in.prof_ok != 0 && *p_in.nletters <= kMaxLetters) != PROF) return;
+#endif
+    fill_body<KT, STORE, PROF>(p_in);
 }
 
 // score-only: maxPos from the per-row best cells -- among the rows whose best score equals the

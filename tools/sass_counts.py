@@ -24,11 +24,13 @@ for l in out.split("\n"):
 FMA = ("IMAD", "IDP")
 ALU = ("VIADDMNMX", "VIMNMX3", "VIMNMX", "LOP3", "SEL", "ISETP", "IADD3", "VIADD", "SHF", "PRMT", "LEA", "IABS", "FLO", "POPC", "MOV", "CS2R", "R2P", "P2R", "PLOP3")
 LSU = ("SHFL", "LDS", "STS", "LDG", "STG", "LD", "ST", "CCTL", "ATOMS", "RED", "ATOMG")
-names = {"swb_tall11fill_kernelILi64ELb1ELb1": "swb_tall::fill_kernel<64,store,look-up>  (single pair, full fill, 3 rows per lane)",
-         "swb_tall11fill_kernelILi64ELb1ELb0": "swb_tall::fill_kernel<64,store,compare>  (single pair, > 7 letters)",
-         "swb_tall11fill_kernelILi64ELb0ELb1": "swb_tall::fill_kernel<64,score-only,look-up>  (single pair)",
-         "3swb11fill_kernelILi64ELb0ELb1": "swb::fill_kernel<64,score-only,look-up>  (batch, 2 rows per lane)",
-         "3swb11fill_kernelILi32ELb1ELb1": "swb::fill_kernel<32,store,look-up>  (batch, 2 rows per lane)"}
+# (single pairs: one kernel per form of the cell arithmetic; batches: one kernel holds both forms -- the look-up form is
+#  the one reported there: its fast group is the one with IDP.4A)
+names = {"swb_tall16fill_kernel_formILi64ELb1ELb1": "swb_tall::fill_kernel_form<64,store,look-up>  (single pair, full fill, 3 rows per lane, half skew)",
+         "swb_tall16fill_kernel_formILi64ELb1ELb0": "swb_tall::fill_kernel_form<64,store,compare>  (single pair, > 7 letters)",
+         "swb_tall16fill_kernel_formILi64ELb0ELb1": "swb_tall::fill_kernel_form<64,score-only,look-up>  (single pair)",
+         "3swb11fill_kernelILi64ELb0EEE": "swb::fill_kernel<64,score-only>, look-up form  (batch, 2 rows per lane)",
+         "3swb11fill_kernelILi32ELb1EEE": "swb::fill_kernel<32,store>, look-up form  (batch, 2 rows per lane)"}
 ROWS = {"swb_tall": 3, "3swb": 2}
 res, lines = {}, []
 for fn, ins in funcs.items():
@@ -42,7 +44,8 @@ for fn, ins in funcs.items():
         cur.append(op.split(".")[0])
         if op.startswith(("BRA", "EXIT", "BSYNC", "BSSY", "RET")):
             blocks.append(cur); cur = []
-    cand = [b for b in blocks if b.count("SHFL") >= 12 and "WARPSYNC" not in b]
+    lookup = "Lb0EEEvNS" not in fn or "fill_kernelI" in fn         # (the compare form has no IDP.4A)
+    cand = [b for b in blocks if b.count("SHFL") >= 12 and "WARPSYNC" not in b and (("IDP" in b) == lookup)]
     if not cand:
         continue
     b = min(cand, key=lambda b: (b.count("SEL") / max(b.count("SHFL"), 1), -len(b)))
@@ -50,9 +53,7 @@ for fn, ins in funcs.items():
     # cells in the block: one VIMNMX3 per cell (profile) or three VIADDMNMX per cell (compare); a block holds whole
     # steps of cell arithmetic plus the shuffles / stores of the step that straddles its first branch
     rows = 3 if "swb_tall" in fn else 2
-    ncell = c["VIMNMX3"] if "Lb1EEE" in fn else c["VIADDMNMX"] / 3.0
-    if "Lb0ELb1EEE" in fn:                 # score-only also tracks the row maxima with VIMNMX3 (2 per row and step)
-        ncell = c["IDP"]
+    ncell = c["IDP"] if lookup else c["VIADDMNMX"] / 3.0       # one IDP.4A per cell (look-up) / three VIADDMNMX per cell (compare)
     steps = ncell / (4.0 * rows)
     alu = sum(v for k, v in c.items() if k in ALU); fma = sum(v for k, v in c.items() if k in FMA)
     lsu = sum(v for k, v in c.items() if k in LSU)
@@ -64,7 +65,7 @@ for fn, ins in funcs.items():
     lines.append(f"{names[key]}\n  fast interior block: {len(b)} instructions ~ {steps:.2f} steps\n"
                  f"  per step: ALU pipe {alu / steps:.1f}  FMA pipe {fma / steps:.1f}  LSU/MIO {lsu / steps:.1f}  total {len(b) / steps:.1f}\n"
                  f"  per cell: ALU {alu / cells:.2f}  all {len(b) / cells:.2f}\n  mix: {dict(c.most_common(14))}\n")
-so = res.get(names["swb_tall11fill_kernelILi64ELb0ELb1"])
+so = res.get(names["swb_tall16fill_kernel_formILi64ELb0ELb1"])
 summary = {"score_only_alu_ops_per_cell": so["alu_ops_per_cell"] if so else None, "kernels": res,
            "source": "cuobjdump -sass of smith-waterman_b200/libswb200.so (tools/sass_counts.py)"}
 (ROOT / "profiles" / "r02_sass_counts.json").write_text(json.dumps(summary, indent=1))
