@@ -18,9 +18,10 @@ BASELINE.json configs[4]) are reported as secondary records.
 
 value  = cols*rows / max-over-ranks(step time) / 1e9 with the sequences already in HBM
          (CUDA events on the launching stream, barrier + synchronize on both sides).  At N=1 the K
-         timed steps run as a pipeline over two H/P buffer sets: the backtrack of step k (a serial
-         pointer chase that occupies one SM) overlaps the fill of step k+1 on a second stream; nothing
-         is skipped.  `serial` repeats the measurement one step at a time (the latency of a step).
+         timed steps run as a pipeline over three H/P buffer sets: the fills of consecutive steps
+         alternate between two streams (the wavefront of step k+1 starts on the SMs the ramp-down of
+         step k leaves idle) and the backtrack of step k (a serial pointer chase that occupies one SM)
+         runs on a third; nothing is skipped.  `serial` repeats the measurement one step at a time (the latency of a step).
          At N>1 the same pipeline runs over three sets of strip buffers per GPU;
 e2e    = the same metric through the host-buffer C-ABI call (swb_ctx_align): H2D of a and
          b, fill, backtrack and the delivery of int32 H and P (16.2 GB) into the caller's pinned host
@@ -461,7 +462,7 @@ def run_single(args, torch, swb, dev, local):
         parity = {"golden": "tests/golden/large_digests.json (CPU oracle)", "digests_checked": checked, "digest_mismatches": bad,
                   "maxPos_ok": maxPos == g["maxPos"], "path_len_ok": plen == g["path_len"]}
 
-    # ---- (2) the same K steps as a pipeline: two H/P buffer sets, the backtrack of step k (a serial pointer chase on
+    # ---- (2) the same K steps as a pipeline: three H/P buffer sets, two fill streams, the backtrack of step k (a serial pointer chase on
     # ONE SM) runs on a high-priority stream beside the fill of step k+1.  Every step still does all of its work; the
     # timed region ends when the last backtrack has finished.  This is the throughput figure (`value`).
     pipelined = not args.no_pipeline
@@ -713,7 +714,7 @@ def run_strips(args, torch, dist, swb, dev, local, rank, world):
     fill_ms_serial = list(fill_ms)
     maxPos, plen = result["maxPos"], result["path_len"]
 
-    # ---- (2) the same K steps as a pipeline over two sets of strip buffers (as at N = 1): the maxPos all-gather and the
+    # ---- (2) the same K steps as a pipeline over three sets of strip buffers (as at N = 1): the maxPos all-gather and the
     # backtrack hops of step k run on a second stream while the fill kernels of step k+1 are already running; every step
     # still does all of its work and the timed region ends when the last backtrack has finished.
     pipelined = not args.no_pipeline
