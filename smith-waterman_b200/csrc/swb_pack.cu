@@ -211,11 +211,18 @@ namespace swb_packed {
 
 struct Chunk { long long r_lo, r_hi; cudaEvent_t ev; };
 
+struct PackSource {                    // pack chunk by chunk in front of every copy (nullptr dH: the rows are packed already)
+    const int32_t* dH = nullptr; const int32_t* dP = nullptr; long long pitch = 0;
+    unsigned char* d_packed_w = nullptr; int* d_flag = nullptr; int32_t* d_base = nullptr; int32_t* h_base = nullptr;
+};
+
 // Copies the packed rows [0, nrows) from d_packed to h_packed in `nchunks` pieces on `st` (events recorded after each),
-// and expands every piece into H / P on `threads` host threads while the later pieces are still in flight.
+// and expands every piece into H / P on `threads` host threads while the later pieces are still in flight.  With a
+// PackSource every piece is packed right in front of its copy, so the first piece is on its way after 1/nchunks of the
+// packing pass instead of after all of it.
 int copy_and_expand(const unsigned char* d_packed, unsigned char* h_packed, long long packed_pitch, long long nrows, long long cols,
                     int32_t* H, int32_t* P, long long pitch, const int32_t* row_base, cudaStream_t st, int device, int threads,
-                    int nchunks)
+                    int nchunks, const PackSource* src = nullptr)
 {
     if (threads <= 0) threads = swb_host_threads();
     nchunks = (int)std::max<long long>(1, std::min<long long>(nchunks, nrows));
@@ -225,6 +232,14 @@ int copy_and_expand(const unsigned char* d_packed, unsigned char* h_packed, long
         Chunk& c = chunks[k];
         c.r_lo = nrows * k / nchunks; c.r_hi = nrows * (k + 1) / nchunks; c.ev = nullptr;
         err = cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming);
+        if (err == cudaSuccess && src != nullptr && src->dH != nullptr) {
+            if (swb_pack_rows_async(src->dH, src->dP, src->pitch, c.r_lo, c.r_hi - c.r_lo, cols, src->d_packed_w + c.r_lo * packed_pitch,
+                                    packed_pitch, src->d_flag, src->d_base + c.r_lo, device, st) != SWB_OK)
+                err = cudaErrorUnknown;
+            if (err == cudaSuccess)
+                err = cudaMemcpyAsync(src->h_base + c.r_lo, src->d_base + c.r_lo, (size_t)(c.r_hi - c.r_lo) * sizeof(int32_t),
+                                      cudaMemcpyDeviceToHost, st);
+        }
         if (err == cudaSuccess)
             err = cudaMemcpyAsync(h_packed + c.r_lo * packed_pitch, d_packed + c.r_lo * packed_pitch,
                                   (size_t)(c.r_hi - c.r_lo) * packed_pitch, cudaMemcpyDeviceToHost, st);
@@ -291,16 +306,16 @@ int swb_d2h_packed(const int32_t* dH, const int32_t* dP, int64_t pitch, int64_t 
     int rc = SWB_OK;
     auto fail = [&](int code) { if (cur != device) cudaSetDevice(cur); return code; };
     if (cudaMemsetAsync(d_flag, 0, sizeof(int), st) != cudaSuccess) return fail(SWB_ERR_CUDA);
-    rc = swb_pack_rows_async(dH, dP, pitch, 0, nrows, cols, d_packed, pp, d_flag, d_base, device, st);
+    // pack, copy and expand chunk by chunk; whether every value fitted the format is known only after the last
+    // chunk -- if one did not (exotic scoring), the plain copies below overwrite whatever was expanded
+    swb_packed::PackSource src;
+    src.dH = dH; src.dP = dP; src.pitch = pitch; src.d_packed_w = d_packed; src.d_flag = d_flag; src.d_base = d_base; src.h_base = h_base;
+    rc = swb_packed::copy_and_expand(d_packed, h_packed, pp, nrows, cols, H, P, host_pitch, h_base, st, device, threads, 24, &src);
     if (rc != SWB_OK) return fail(rc);
-    // the row bases and the flag sit behind the packed rows: one small copy, then the verdict
-    if (cudaMemcpyAsync(h_base, d_base, base_bytes + sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+    if (cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess)
         return fail(SWB_ERR_CUDA);
-    if (*h_flag == 0) {
-        rc = swb_packed::copy_and_expand(d_packed, h_packed, pp, nrows, cols, H, P, host_pitch, h_base, st, device, threads, 24);
-    } else {
-        // some row step of H or some P value does not fit the byte format (exotic scoring): plain copies
+    if (*h_flag != 0) {
         cudaError_t e = cudaSuccess;
         if (H) e = cudaMemcpy2DAsync(H, (size_t)host_pitch * 4, dH, (size_t)pitch * 4, (size_t)cols * 4, (size_t)nrows, cudaMemcpyDeviceToHost, st);
         if (P && e == cudaSuccess) e = cudaMemcpy2DAsync(P, (size_t)host_pitch * 4, dP, (size_t)pitch * 4, (size_t)cols * 4, (size_t)nrows, cudaMemcpyDeviceToHost, st);
